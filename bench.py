@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: V-cycle ms & HBM GB/s (fraction of peak) at N=16384^2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Own arm.  Workload = BASELINE.json configs[2] (SURVEY.md 8d "C3"): N=16384, nu=-4e-4, vscale=1,
+tol=1e-6, V-cycle, reference initial conditions generated on the device (synthetic, resident in
+HBM before the timed region).  One STEP = one implicit Crank-Nicolson time step = compute_rhs +
+mg_outer (V-cycles until ||r||/||r0|| <= tol; multigrid.cpp:165-169).  `value` = timed ms divided
+by the V-cycles executed in the timed region, i.e. ms per V-cycle INCLUDING its convergence check
+and the amortised compute_rhs of its time step.  Fields are 2.1 GB each (>> 126 MB L2), so no
+L2 flush is needed between iterations.
+
+`e2e` = the same metric through the reference-facing entry point mgb200_timestepper_host
+(timestepper(uT,u0,v1,v2,...) of multigrid.cpp:124 with HOST arrays, pinned): tower allocation,
+H2D of u0,v1,v2, one time step, D2H of uT, all inside the timed region, every step.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libmgref_O3.so: the
+unmodified gs.cpp + multigrid.cpp, run inside an OpenMP team as multigrid.cpp:252-258 does) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FULL = 16384
+NU, VSCALE, TOL = -4e-4, 1.0, 1e-6
+METRIC = "V-cycle ms at N=16384^2 (fine-grid V-cycle incl. convergence check)"
+W_REF_BYTES_PER_NODE = 475.0          # reference pass structure, one pass per operator
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock + throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the compiled reference (or the oracle port) on a bounded sample
+def cpu_vcycle_ms(steps, warmup, threads=None):
+    import numpy as np
+    import psutil
+    from oracle.oracle import Oracle, OracleSolver, Towers, ref_available
+    threads = threads or os.cpu_count() or 1
+    free_gb = psutil.virtual_memory().available / 2**30
+    n = 8192 if free_gb > 24 else 4096
+    scale = (N_FULL + 1) ** 2 / float((n + 1) ** 2)
+    dx = 1.0 / n; dt = dx / 10
+    o = Oracle()
+    u0, v1, v2 = o.initial_conditions(n, VSCALE)
+    times = []
+    if ref_available("O3"):
+        kind = "reference"
+        tw = Towers(Oracle("O3"), n, u0, v1, v2, NU, dt, dx, TOL, 1)
+        del u0, v1, v2
+        tw.form_rhs()
+        for k in range(warmup + steps):
+            t = time.perf_counter()
+            tw.cycle_and_norm(threads)
+            if k >= warmup:
+                times.append(time.perf_counter() - t)
+    else:
+        kind, threads = "port", 1
+        s = OracleSolver(n, u0, v1, v2, NU, dt, dx, TOL, 1)
+        s.form_rhs()
+        for k in range(warmup + steps):
+            t = time.perf_counter()
+            s.cycle(); s.residual_norm()
+            if k >= warmup:
+                times.append(time.perf_counter() - t)
+    ms = 1e3 * float(np.mean(times)) * scale
+    sample = (f"{steps} V-cycle(s)+check at N={n} after {warmup} warm-up, mean x{scale:.3f} "
+              f"(node count ratio to N={N_FULL}); {'gs.cpp+multigrid.cpp -O3, OpenMP tasks' if kind == 'reference' else 'oracle/mg_oracle.c -O2, serial'}")
+    return ms, kind, threads, sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ms, kind, cores, sample = cpu_vcycle_ms(max(1, args.steps), max(0, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference initial conditions, multigrid.cpp:206-233)",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "effective_GBps_Wref": W_REF_BYTES_PER_NODE * (N_FULL + 1) ** 2 / (ms * 1e-3) / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(gpus):
+    return {"workload": f"C3: N={N_FULL}^2 advection-diffusion Crank-Nicolson step, nu={NU}, vscale={VSCALE}, "
+                        f"tol={TOL}, V-cycle (3 pre + 3 post RB-GS), {gpus} GPU(s)",
+            "N": N_FULL, "nu": NU, "vscale": VSCALE, "tol": TOL, "shape": 1, "levels": 10,
+            "l2_policy": "inputs (2.1 GB per field) exceed the 126 MB L2; no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_own(args, rank, world):
+    import torch
+    import hpcclassmultigridproject_b200 as mg
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    plan = mg.PLAN_UNFUSED if args.plan == "unfused" else mg.PLAN_FUSED
+    arith = mg.ARITH_EXACT if args.arith == "exact" else mg.ARITH_FAST
+    n = args.n
+    dx = 1.0 / n; dt = dx / 10
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    s = mg.Solver(n, NU, dt, dx, TOL, plan=plan, arith=arith, device=local)
+    s.set_fields_reference_ic(VSCALE)
+    s.synchronize()
+    for _ in range(args.warmup):
+        s.timestep(1)
+    barrier()
+    l0 = s.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ext = torch.cuda.ExternalStream(s.stream)
+    with ClockSampler(local) as clk:
+        ev0.record(ext)
+        infos = s.timestep(args.steps)
+        ev1.record(ext)
+        ev1.synchronize()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    if dist:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    cycles = sum(i.cycles for i in infos)
+    launches = s.kernel_launches - l0
+    ms_cycle = ms_total / max(1, cycles)
+    m0 = float(n + 1) ** 2
+
+    # dominant kernel: the level-0 streaming pass (fused) / colour half-sweep (unfused)
+    prof = s.profile_level0(reps=5)
+    (ms_a, by_a), (ms_b, by_b) = prof
+    dom_ms, dom_bytes = (ms_a + ms_b) / 2, (by_a + by_b) / 2
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"{args.plan}_level0_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cycle_bytes = s.cycle_bytes
+    s.close()
+
+    # ---- e2e through the reference-facing entry point, host buffers, copies timed ----------
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        d = [torch.empty(n + 1, n + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
+        mg.ops.initial_conditions(*d, n, VSCALE)
+        host = [torch.empty(n + 1, n + 1, dtype=torch.float64).pin_memory() for _ in range(4)]
+        for h, t in zip(host, d):
+            h.copy_(t)
+        del d
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+        reps, tt, cyc = max(1, min(args.steps, 3)), [], 0
+        for k in range(1 + reps):
+            t0 = time.perf_counter()
+            info = mg.timestepper_host(host[3], host[0], host[1], host[2], NU, mg.maxlvl_for(n), n, dt, dt, dx, TOL, 1,
+                                       plan=plan, arith=arith, device=local)
+            el = time.perf_counter() - t0
+            if k >= 1:
+                tt.append(el); cyc += info.cycles
+        e2e = {"value": 1e3 * sum(tt) / max(1, cyc), "unit": "ms", "h2d_bytes_per_step": int(3 * m0 * 8),
+               "d2h_bytes_per_step": int(m0 * 8), "call": "mgb200_timestepper_host (timestepper, multigrid.cpp:124), T=dt",
+               "ms_per_call": 1e3 * sum(tt) / len(tt), "cycles_per_call": cyc / len(tt)}
+        del host
+    if world > 1 and e2e is None and rank == 0:
+        e2e = None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ms, kind, cores, sample = cpu_vcycle_ms(2, 1)
+        cpu = {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": ms_cycle, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (reference initial conditions, multigrid.cpp:206-233, generated on device)",
+            "config": dict(workload_config(world), N=n, plan=args.plan, arith=args.arith,
+                           step="one implicit time step = compute_rhs + V-cycles to tol; value = ms / V-cycles"),
+            "cycles_per_step": cycles / args.steps, "vcycles_timed": cycles,
+            "effective_GBps_Wref": W_REF_BYTES_PER_NODE * m0 / (ms_cycle * 1e-3) / 1e9,
+            "plan_GBps": cycle_bytes / (ms_cycle * 1e-3) / 1e9, "plan_bytes_per_cycle": cycle_bytes,
+            "plan_frac_of_hbm_peak": cycle_bytes / (ms_cycle * 1e-3) / 1e9 / hbm_peak,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": ("level-0 streaming pass (3 RB-GS iterations fused with residual+injection / "
+                                    "prolong+correct+norm)") if args.plan == "fused" else "level-0 colour half-sweep + residual",
+                         "launch_ms": [ms_a, ms_b], "launch_bytes": [by_a, by_b]},
+            "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL)
+    ap.add_argument("--plan", default="fused", choices=["fused", "unfused"])
+    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_own(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,460 @@
+// ops_basic.cu -- one-operator-per-launch kernels, layout-generic (see ops_basic.cuh).
+//
+// Thread mapping: threadIdx.x runs along the contiguous (column) index, a block covers
+// ROWS_PER_BLOCK rows x 256 columns; blockIdx.x indexes row groups (no 65535 limit), blockIdx.y
+// column chunks.  Every global access of a warp is a unit-stride run (split layout: one run
+// per parity).
+#include "ops_basic.cuh"
+
+namespace mgb200 {
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int ROWS_PER_BLOCK = 8;
+
+inline dim3 tile_grid(long rows, long cols)
+{
+    return dim3((unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (unsigned)((cols + TPB - 1) / TPB), 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void __launch_bounds__(TPB) k_gs_colour(double* __restrict__ u, const double* __restrict__ rhs,
+                                                   const double* __restrict__ v1, const double* __restrict__ v2,
+                                                   long n, Layout L, Stencil st, int colour)
+{
+    const long k = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = 1 + (long)blockIdx.x * ROWS_PER_BLOCK;
+#pragma unroll 2
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i >= n) break;
+        const long p = (i + colour) & 1;      // column parity of this colour in row i
+        const long j = 2 * k + 2 - p;         // p=1: 1,3,5,...   p=0: 2,4,6,...
+        if (j >= n) continue;
+        const long q = L.at(i, j);
+        const Coef4 c = Arith<ARITH>::coef(v1[q], v2[q], st);
+        u[q] = Arith<ARITH>::gs(rhs[q], u[L.at(i - 1, j)], u[L.at(i, j - 1)], u[L.at(i + 1, j)],
+                                u[L.at(i, j + 1)], c, st);
+    }
+}
+
+// MODE bit0: write res, bit1: accumulate squares into partials
+template <int ARITH, int MODE>
+__global__ void __launch_bounds__(TPB) k_residual(double* __restrict__ res, const double* __restrict__ u,
+                                                  const double* __restrict__ rhs, const double* __restrict__ v1,
+                                                  const double* __restrict__ v2, long n, Layout L, Stencil st,
+                                                  double* __restrict__ partials)
+{
+    __shared__ double scratch[32];
+    const long j = 1 + (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = 1 + (long)blockIdx.x * ROWS_PER_BLOCK;
+    double acc = 0.0;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i >= n || j >= n) break;
+        const long q = L.at(i, j);
+        const Coef4 c = Arith<ARITH>::coef(v1[q], v2[q], st);
+        const double rv = Arith<ARITH>::residual(rhs[q], u[q], u[L.at(i - 1, j)], u[L.at(i, j - 1)],
+                                                 u[L.at(i + 1, j)], u[L.at(i, j + 1)], c, st);
+        if (MODE & 1) res[q] = rv;
+        if (MODE & 2) acc += rv * rv;
+    }
+    if (MODE & 2) {
+        const double t = block_sum(acc, scratch);
+        if (threadIdx.x == 0) partials[(long)blockIdx.x * gridDim.y + blockIdx.y] = t;
+    }
+}
+
+template <int ARITH, bool WITH_RES0>
+__global__ void __launch_bounds__(TPB) k_compute_rhs(double* __restrict__ rhs, const double* __restrict__ u,
+                                                     const double* __restrict__ v1, const double* __restrict__ v2,
+                                                     long n, Layout L, Stencil st, double* __restrict__ partials)
+{
+    __shared__ double scratch[32];
+    const long j = 1 + (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = 1 + (long)blockIdx.x * ROWS_PER_BLOCK;
+    double acc = 0.0;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i >= n || j >= n) break;
+        const long q = L.at(i, j);
+        const Coef4 c = Arith<ARITH>::coef(v1[q], v2[q], st);
+        const double uc = u[q], up = u[L.at(i - 1, j)], lf = u[L.at(i, j - 1)], dn = u[L.at(i + 1, j)],
+                     rt = u[L.at(i, j + 1)];
+        const double f = Arith<ARITH>::rhs(uc, up, lf, dn, rt, c, st);
+        rhs[q] = f;
+        if (WITH_RES0) {
+            const double rv = Arith<ARITH>::residual(f, uc, up, lf, dn, rt, c, st);
+            acc += rv * rv;
+        }
+    }
+    if (WITH_RES0) {
+        const double t = block_sum(acc, scratch);
+        if (threadIdx.x == 0) partials[(long)blockIdx.x * gridDim.y + blockIdx.y] = t;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_square_partials(const double* __restrict__ a, long n, Layout L,
+                                                         double* __restrict__ partials)
+{
+    __shared__ double scratch[32];
+    const long j = 1 + (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = 1 + (long)blockIdx.x * ROWS_PER_BLOCK;
+    double acc = 0.0;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i >= n || j >= n) break;
+        const double x = a[L.at(i, j)];
+        acc += x * x;
+    }
+    const double t = block_sum(acc, scratch);
+    if (threadIdx.x == 0) partials[(long)blockIdx.x * gridDim.y + blockIdx.y] = t;
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_partials(const double* __restrict__ partials, long count,
+                                                          double* __restrict__ out)
+{
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (long q = threadIdx.x; q < count; q += 1024) acc += partials[q];
+    const double t = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+template <bool INTERIOR>
+__global__ void __launch_bounds__(TPB) k_restrict(double* __restrict__ coarse, Layout Lc,
+                                                  const double* __restrict__ fine, Layout Lf, long nc)
+{
+    const long lo = INTERIOR ? 1 : 0, hi = INTERIOR ? nc - 1 : nc;
+    const long J = lo + (long)blockIdx.y * TPB + threadIdx.x;
+    const long I0 = lo + (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long I = I0 + r;
+        if (I > hi || J > hi) break;
+        coarse[Lc.at(I, J)] = fine[Lf.at(2 * I, 2 * J)];
+    }
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(TPB) k_prolong(double* __restrict__ fine, Layout Lf,
+                                                 const double* __restrict__ coarse, Layout Lc, long nc)
+{
+    const long nf = 2 * nc;
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > nf || j > nf) break;
+        const long I = i >> 1, J = j >> 1;
+        const double c00 = coarse[Lc.at(I, J)];
+        double v;
+        if ((i & 1) == 0 && (j & 1) == 0) {
+            v = c00;                                                                  // gs.cpp:238
+        } else if ((i & 1) == 1 && (j & 1) == 0) {
+            v = __dmul_rn(__dadd_rn(c00, coarse[Lc.at(I + 1, J)]), 0.5);            // gs.cpp:239
+        } else if ((i & 1) == 0) {
+            v = __dmul_rn(__dadd_rn(c00, coarse[Lc.at(I, J + 1)]), 0.5);            // gs.cpp:240
+        } else {
+            double t = __dadd_rn(c00, coarse[Lc.at(I + 1, J)]);                     // gs.cpp:241
+            t = __dadd_rn(t, coarse[Lc.at(I, J + 1)]);
+            t = __dadd_rn(t, coarse[Lc.at(I + 1, J + 1)]);
+            v = __dmul_rn(t, 0.25);
+        }
+        const long q = Lf.at(i, j);
+        fine[q] = ADD ? __dadd_rn(fine[q], v) : v;                                    // multigrid.cpp:83
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_vecadd(double* __restrict__ c, const double* __restrict__ a,
+                                                const double* __restrict__ b, long n, Layout L)
+{
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > n || j > n) break;
+        const long q = L.at(i, j);
+        c[q] = __dadd_rn(a[q], b[q]);
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_convert(double* __restrict__ dst, Layout Ld, const double* __restrict__ src,
+                                                 Layout Ls, long n)
+{
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > n || j > n) break;
+        dst[Ld.at(i, j)] = src[Ls.at(i, j)];
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_initial_conditions(double* __restrict__ u0, double* __restrict__ v1,
+                                                            double* __restrict__ v2, long n, Layout L, double vscale)
+{
+    const double PI = 3.1415926535897932;                    // multigrid.cpp:14
+    const double x0 = 0.2, y0 = 0.4, sigma = 100.0;          // multigrid.cpp:206-207
+    const double kx = 1.0 * PI, ky = 1.0 * PI;
+    const double dx = 1.0 / (double)n;
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > n || j > n) break;
+        const double x = i * dx, y = j * dx;
+        double g = exp(-sigma * ((x - x0) * (x - x0) + (y - y0) * (y - y0)));        // multigrid.cpp:219
+        // boundary lines zeroed with a loop bound of N: node (N,0) keeps its value (multigrid.cpp:227-233)
+        const bool zeroed = (i == 0 && j < n) || (j == n && i < n) || (i == n && j >= 1) || (j == 0 && i < n);
+        if (zeroed) g = 0.0;
+        const long q = L.at(i, j);
+        u0[q] = g;
+        v1[q] = (-ky * sin(kx * i * dx) * cos(ky * j * dx)) * vscale;                // multigrid.cpp:222
+        v2[q] = (kx * cos(kx * i * dx) * sin(ky * j * dx)) * vscale;                 // multigrid.cpp:223
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_tower_flat(double* __restrict__ flat_out, const double* __restrict__ src,
+                                                    int from_level0, Layout L0, long N)
+{
+    const long h = N / 2, q = N / 4;
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > q || j > q) break;
+        const long f = 2 * i * (h + 1) + 2 * j;              // flat index into the source (gs.cpp:283, n = N/2)
+        double v;
+        if (from_level0) v = src[L0.at(f / (N + 1), f % (N + 1))];   // level 0 is a dense (N+1)^2 array
+        else v = src[f];
+        flat_out[i * (q + 1) + j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_flat_to_level(double* __restrict__ dst, Layout Ld,
+                                                       const double* __restrict__ flat, long nl)
+{
+    const long j = (long)blockIdx.y * TPB + threadIdx.x;
+    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long i = i0 + r;
+        if (i > nl || j > nl) break;
+        dst[Ld.at(i, j)] = flat[i * (nl + 1) + j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Coarsest level on ONE thread block, all fields staged in shared memory (natural order).
+template <int ARITH>
+__global__ void __launch_bounds__(1024) k_coarse_solve(double* __restrict__ u, const double* __restrict__ rhs,
+                                                       const double* __restrict__ v1, const double* __restrict__ v2,
+                                                       int n, Layout L, Stencil st, int zero_init, int maxit,
+                                                       double tol, int* __restrict__ iters_out)
+{
+    extern __shared__ double sm[];
+    __shared__ double scratch[32];
+    __shared__ double s_norm2;
+    const int ld = n + 1, m = ld * ld;
+    double* su = sm;
+    double* sf = sm + m;
+    double* s1 = sm + 2 * m;
+    double* s2 = sm + 3 * m;
+    for (int q = threadIdx.x; q < m; q += blockDim.x) {
+        const int i = q / ld, j = q % ld;
+        const long g = L.at(i, j);
+        su[q] = zero_init ? 0.0 : u[g];
+        sf[q] = rhs[g];
+        s1[q] = v1[g];
+        s2[q] = v2[g];
+    }
+    __syncthreads();
+    const int ni = n - 1, npts = ni * ni;
+    int it = 0;
+    double rn = 1.0;                                                     // multigrid.cpp:58
+    while (it < maxit && rn > tol) {                                     // multigrid.cpp:60
+        for (int colour = 0; colour < 2; ++colour) {
+            for (int p = threadIdx.x; p < npts; p += blockDim.x) {
+                const int i = 1 + p / ni, j = 1 + p % ni;
+                if (((i + j) & 1) != colour) continue;
+                const int q = i * ld + j;
+                const Coef4 c = Arith<ARITH>::coef(s1[q], s2[q], st);
+                su[q] = Arith<ARITH>::gs(sf[q], su[q - ld], su[q - 1], su[q + ld], su[q + 1], c, st);
+            }
+            __syncthreads();
+        }
+        double acc = 0.0;
+        for (int p = threadIdx.x; p < npts; p += blockDim.x) {
+            const int i = 1 + p / ni, j = 1 + p % ni;
+            const int q = i * ld + j;
+            const Coef4 c = Arith<ARITH>::coef(s1[q], s2[q], st);
+            const double rv = Arith<ARITH>::residual(sf[q], su[q], su[q - ld], su[q - 1], su[q + ld], su[q + 1], c, st);
+            acc += rv * rv;
+        }
+        const double t = block_sum(acc, scratch);
+        if (threadIdx.x == 0) s_norm2 = t;
+        __syncthreads();
+        rn = sqrt(s_norm2);
+        ++it;
+        __syncthreads();
+    }
+    for (int p = threadIdx.x; p < npts; p += blockDim.x) {
+        const int i = 1 + p / ni, j = 1 + p % ni;
+        u[L.at(i, j)] = su[i * ld + j];
+    }
+    if (zero_init) {   // the boundary of a freshly zeroed level is zero as well (multigrid.cpp:77)
+        for (int q = threadIdx.x; q <= n; q += blockDim.x) {
+            u[L.at(0, q)] = 0.0; u[L.at(n, q)] = 0.0; u[L.at(q, 0)] = 0.0; u[L.at(q, n)] = 0.0;
+        }
+    }
+    if (threadIdx.x == 0 && iters_out) *iters_out = it;
+}
+
+}  // namespace
+
+int ops_basic_init()
+{
+    static bool done = false;
+    if (done) return MGB200_OK;
+    const int smem = 4 * 65 * 65 * (int)sizeof(double);
+    MGB_CUDA(cudaFuncSetAttribute(k_coarse_solve<MGB200_ARITH_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MGB_CUDA(cudaFuncSetAttribute(k_coarse_solve<MGB200_ARITH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+    return MGB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+long residual_partials_count(long n)
+{
+    dim3 g = tile_grid(n - 1, n - 1);
+    return (long)g.x * g.y;
+}
+
+int launch_gs_colour(double* u, const double* rhs, const double* v1, const double* v2, long n, Layout L,
+                     const Stencil& st, int colour, int arith, cudaStream_t s)
+{
+    if (n < 2) return MGB200_OK;
+    dim3 g = tile_grid(n - 1, (n - 1 + 1) / 2);
+    if (arith == MGB200_ARITH_EXACT)
+        k_gs_colour<MGB200_ARITH_EXACT><<<g, TPB, 0, s>>>(u, rhs, v1, v2, n, L, st, colour);
+    else
+        k_gs_colour<MGB200_ARITH_FAST><<<g, TPB, 0, s>>>(u, rhs, v1, v2, n, L, st, colour);
+    return check_launch("k_gs_colour");
+}
+
+int launch_residual(double* res, const double* u, const double* rhs, const double* v1, const double* v2,
+                    long n, Layout L, const Stencil& st, int arith, double* partials, cudaStream_t s)
+{
+    if (n < 2) return MGB200_OK;
+    dim3 g = tile_grid(n - 1, n - 1);
+    const int mode = (res ? 1 : 0) | (partials ? 2 : 0);
+    if (mode == 0) return fail(MGB200_ERR_INVALID, "launch_residual: nothing to produce");
+#define MGB_RES(A, M) k_residual<A, M><<<g, TPB, 0, s>>>(res, u, rhs, v1, v2, n, L, st, partials)
+    if (arith == MGB200_ARITH_EXACT) {
+        if (mode == 1) MGB_RES(MGB200_ARITH_EXACT, 1); else if (mode == 2) MGB_RES(MGB200_ARITH_EXACT, 2); else MGB_RES(MGB200_ARITH_EXACT, 3);
+    } else {
+        if (mode == 1) MGB_RES(MGB200_ARITH_FAST, 1); else if (mode == 2) MGB_RES(MGB200_ARITH_FAST, 2); else MGB_RES(MGB200_ARITH_FAST, 3);
+    }
+#undef MGB_RES
+    return check_launch("k_residual");
+}
+
+int launch_compute_rhs(double* rhs, const double* u, const double* v1, const double* v2, long n, Layout L,
+                       const Stencil& st, int arith, double* partials, cudaStream_t s)
+{
+    if (n < 2) return MGB200_OK;
+    dim3 g = tile_grid(n - 1, n - 1);
+    if (arith == MGB200_ARITH_EXACT) {
+        if (partials) k_compute_rhs<MGB200_ARITH_EXACT, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+        else k_compute_rhs<MGB200_ARITH_EXACT, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+    } else {
+        if (partials) k_compute_rhs<MGB200_ARITH_FAST, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+        else k_compute_rhs<MGB200_ARITH_FAST, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+    }
+    return check_launch("k_compute_rhs");
+}
+
+int launch_square_partials(const double* a, long n, Layout L, double* partials, cudaStream_t s)
+{
+    dim3 g = tile_grid(n - 1, n - 1);
+    k_square_partials<<<g, TPB, 0, s>>>(a, n, L, partials);
+    return check_launch("k_square_partials");
+}
+
+int launch_reduce_partials(const double* partials, long count, double* out, cudaStream_t s)
+{
+    k_reduce_partials<<<1, 1024, 0, s>>>(partials, count, out);
+    return check_launch("k_reduce_partials");
+}
+
+int launch_restrict(double* coarse, Layout Lc, const double* fine, Layout Lf, long nf, cudaStream_t s)
+{
+    const long nc = nf / 2;
+    k_restrict<false><<<tile_grid(nc + 1, nc + 1), TPB, 0, s>>>(coarse, Lc, fine, Lf, nc);
+    return check_launch("k_restrict");
+}
+
+int launch_restrict_interior(double* coarse, Layout Lc, const double* fine, Layout Lf, long nf, cudaStream_t s)
+{
+    const long nc = nf / 2;
+    if (nc < 2) return MGB200_OK;
+    k_restrict<true><<<tile_grid(nc - 1, nc - 1), TPB, 0, s>>>(coarse, Lc, fine, Lf, nc);
+    return check_launch("k_restrict");
+}
+
+int launch_prolong(double* fine, Layout Lf, const double* coarse, Layout Lc, long nc, bool add, cudaStream_t s)
+{
+    dim3 g = tile_grid(2 * nc + 1, 2 * nc + 1);
+    if (add) k_prolong<true><<<g, TPB, 0, s>>>(fine, Lf, coarse, Lc, nc);
+    else k_prolong<false><<<g, TPB, 0, s>>>(fine, Lf, coarse, Lc, nc);
+    return check_launch("k_prolong");
+}
+
+int launch_vecadd(double* c, const double* a, const double* b, long n, Layout L, cudaStream_t s)
+{
+    k_vecadd<<<tile_grid(n + 1, n + 1), TPB, 0, s>>>(c, a, b, n, L);
+    return check_launch("k_vecadd");
+}
+
+int launch_convert(double* dst, Layout Ld, const double* src, Layout Ls, long n, cudaStream_t s)
+{
+    k_convert<<<tile_grid(n + 1, n + 1), TPB, 0, s>>>(dst, Ld, src, Ls, n);
+    return check_launch("k_convert");
+}
+
+int launch_initial_conditions(double* u0, double* v1, double* v2, long n, Layout L, double vscale, cudaStream_t s)
+{
+    k_initial_conditions<<<tile_grid(n + 1, n + 1), TPB, 0, s>>>(u0, v1, v2, n, L, vscale);
+    return check_launch("k_initial_conditions");
+}
+
+int launch_tower_flat(double* flat_out, const double* src, bool from_level0, Layout L0, long N, cudaStream_t s)
+{
+    const long q = N / 4;
+    k_tower_flat<<<tile_grid(q + 1, q + 1), TPB, 0, s>>>(flat_out, src, from_level0 ? 1 : 0, L0, N);
+    return check_launch("k_tower_flat");
+}
+
+int launch_flat_to_level(double* dst, Layout Ld, const double* flat, long nl, cudaStream_t s)
+{
+    k_flat_to_level<<<tile_grid(nl + 1, nl + 1), TPB, 0, s>>>(dst, Ld, flat, nl);
+    return check_launch("k_flat_to_level");
+}
+
+int launch_coarse_solve(double* u, const double* rhs, const double* v1, const double* v2, long n, Layout L,
+                        const Stencil& st, int arith, bool zero_init, int maxit, double tol, int* iters_out,
+                        cudaStream_t s)
+{
+    if (n > 64) return fail(MGB200_ERR_INVALID, "coarse_solve: n > 64 not supported by the single-block kernel");
+    const size_t smem = 4 * (size_t)(n + 1) * (n + 1) * sizeof(double);
+    MGB_TRY(ops_basic_init());
+    if (arith == MGB200_ARITH_EXACT) {
+        k_coarse_solve<MGB200_ARITH_EXACT><<<1, 1024, smem, s>>>(u, rhs, v1, v2, (int)n, L, st, zero_init ? 1 : 0, maxit, tol, iters_out);
+    } else {
+        k_coarse_solve<MGB200_ARITH_FAST><<<1, 1024, smem, s>>>(u, rhs, v1, v2, (int)n, L, st, zero_init ? 1 : 0, maxit, tol, iters_out);
+    }
+    return check_launch("k_coarse_solve");
+}
+
+}  // namespace mgb200

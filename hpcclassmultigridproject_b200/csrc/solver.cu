@@ -1,0 +1,702 @@
+// solver.cu -- the V/W-cycle driver (C++ host side) behind the C ABI of include/mgb200.h.
+//
+// Re-creates the control flow of the reference driver -- mg_inner / mg_outer / timestepper,
+// multigrid.cpp:17-186 (= multigrid.cu:17-200) -- on level towers that live in HBM in the
+// split layout (common.cuh).  Two pass plans produce the same field:
+//   UNFUSED  one launch per reference operator (ops_basic.cu): 2 launches per RB iteration,
+//            residual, injection, zero, prolong+add.   W = 320 B/node/level.
+//   FUSED    one streaming launch per leg (stream_pass.cu): {3 RB iterations + residual +
+//            injection} going down, {prolong + correct + 3 RB iterations (+ residual norm on
+//            level 0)} coming up.                      W = 84 B/node/level.
+// One whole cycle + convergence check is captured into a CUDA graph and replayed; the only
+// host decision per cycle is the comparison of the norm (multigrid.cpp:108), read back through
+// pinned memory.  The coarsest level is solved by one thread block on the device
+// (multigrid.cpp:55-65), so no host round trip happens inside a cycle.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "ops_basic.cuh"
+#include "stream_pass.cuh"
+
+namespace mgb200 {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+long& launch_counter()
+{
+    static thread_local long c = 0;
+    return c;
+}
+
+Stencil make_stencil(double dt, double nu, double dx)
+{
+    // volatile: keep the host compiler from contracting or re-associating; the sequence is the
+    // reference's (gs.cpp:10, :44, :75).
+    volatile double r = 0.5 * dt / (dx * dx);
+    volatile double four_r = 4.0 * r;
+    volatile double four_r_nu = four_r * nu;
+    Stencil s;
+    s.r = r; s.nu = nu; s.h = dx;
+    s.diag = 1.0 - four_r_nu;
+    s.diag_rhs = 1.0 + four_r_nu;
+    s.inv_diag = 1.0 / s.diag;
+    s.hr = r * dx * 0.5;
+    s.rnu = r * nu;
+    return s;
+}
+
+struct Level {
+    long n = 0;
+    Layout L{0, 0};
+    Stencil st{};
+    size_t elems = 0;
+    double* u[2] = {nullptr, nullptr};
+    int cur = 0;                       // which of u[] holds the current iterate
+    double *rhs = nullptr, *v1 = nullptr, *v2 = nullptr;
+};
+
+}  // namespace mgb200
+
+using namespace mgb200;
+
+struct mgb200_solver {
+    long N = 0;
+    int maxlvl = 0;
+    double nu = 0, dt = 0, dx = 0, tol = 0;
+    mgb200_options opt{};
+    int device = 0;
+    std::vector<Level> lv;
+    cudaStream_t stream = nullptr;
+    double* d_partials = nullptr;      // block partial sums of squares
+    long partials_cap = 0;
+    double* d_norm2 = nullptr;         // [0] current ||r||^2
+    double* h_norm2 = nullptr;         // pinned mirror
+    int* d_coarse_iters = nullptr;
+    double* d_flat[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec = nullptr;
+    long graph_kernels = 0;
+    long launches = 0;
+    bool have_fields = false, have_rhs = false;
+    double res0 = 0, res = 0;
+
+    ~mgb200_solver() { release(); }
+    void release();
+    int  init(long n, int maxlvl_, double nu_, double dt_, double dx_, double tol_, const mgb200_options* o);
+    int  build_towers();
+    int  cycle_body(int l);
+    int  smooth(Level& g, int iters);
+    int  residual_norm_level0();
+    int  record_cycle();               // cycle_body(0) + convergence norm, on `stream`
+    int  run_cycle_async();
+    int  read_norm(double* out);
+    int  form_rhs(double* res0_out);
+    int  solve(mgb200_solve_info* info);
+    int  get_u_natural(double* dst_dev, long ld);
+    long count(long before) { long d = launch_counter() - before; launches += d; return d; }
+};
+
+void mgb200_solver::release()
+{
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    for (auto& g : lv) {
+        cudaFree(g.u[0]); cudaFree(g.u[1]); cudaFree(g.rhs); cudaFree(g.v1); cudaFree(g.v2);
+    }
+    lv.clear();
+    cudaFree(d_partials); d_partials = nullptr;
+    cudaFree(d_norm2); d_norm2 = nullptr;
+    cudaFree(d_coarse_iters); d_coarse_iters = nullptr;
+    cudaFree(d_flat[0]); cudaFree(d_flat[1]); d_flat[0] = d_flat[1] = nullptr;
+    if (h_norm2) { cudaFreeHost(h_norm2); h_norm2 = nullptr; }
+    if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+}
+
+int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_, double tol_, const mgb200_options* o)
+{
+    if (o) {
+        if (o->struct_size != (int)sizeof(mgb200_options)) return fail(MGB200_ERR_INVALID, "mgb200_options.struct_size mismatch");
+        opt = *o;
+    } else {
+        mgb200_default_options(&opt);
+    }
+    if (n < 4 || (n & (n - 1)) != 0) return fail(MGB200_ERR_INVALID, "n must be a power of two >= 4");
+    if (maxlvl_ < 1 || (n >> (maxlvl_ - 1)) < 4) return fail(MGB200_ERR_INVALID, "maxlvl out of range for n");
+    if ((n >> (maxlvl_ - 1)) > 64)
+        return fail(MGB200_ERR_INVALID, "coarsest level must have n <= 64 (on-device coarse solve); raise maxlvl");
+    if (opt.shape < 1 || opt.niter < 0 || opt.max_cycle < 0 || opt.max_cycle > 50)
+        return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MGB200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    if (opt.device >= 0) MGB_CUDA(cudaSetDevice(opt.device));
+    MGB_CUDA(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    MGB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MGB200_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                              ", this library is built for sm_100a only");
+    N = n; maxlvl = maxlvl_; nu = nu_; dt = dt_; dx = dx_; tol = tol_;
+    MGB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    MGB_TRY(ops_basic_init());
+    if (opt.plan == MGB200_PLAN_FUSED) MGB_TRY(stream_pass_init());
+    lv.resize(maxlvl);
+    for (int l = 0; l < maxlvl; ++l) {
+        Level& g = lv[l];
+        g.n = n >> l;
+        g.L = split_layout(g.n);
+        g.st = make_stencil(dt, nu, dx * (double)(1L << l));    // dx2 = 2*dx per level (multigrid.cpp:49)
+        g.elems = layout_elems(g.L, g.n);
+        const size_t bytes = g.elems * sizeof(double);
+        MGB_CUDA(cudaMalloc(&g.u[0], bytes));
+        MGB_CUDA(cudaMalloc(&g.u[1], bytes));
+        MGB_CUDA(cudaMalloc(&g.rhs, bytes));
+        MGB_CUDA(cudaMalloc(&g.v1, bytes));
+        MGB_CUDA(cudaMalloc(&g.v2, bytes));
+        MGB_CUDA(cudaMemsetAsync(g.u[0], 0, bytes, stream));
+        MGB_CUDA(cudaMemsetAsync(g.u[1], 0, bytes, stream));
+        MGB_CUDA(cudaMemsetAsync(g.rhs, 0, bytes, stream));     // coarse rhs starts as zeros (multigrid.cpp:159)
+        MGB_CUDA(cudaMemsetAsync(g.v1, 0, bytes, stream));
+        MGB_CUDA(cudaMemsetAsync(g.v2, 0, bytes, stream));
+    }
+    partials_cap = std::max(residual_partials_count(N), stream_pass_tiles(N)) + 8;
+    MGB_CUDA(cudaMalloc(&d_partials, partials_cap * sizeof(double)));
+    MGB_CUDA(cudaMalloc(&d_norm2, 8 * sizeof(double)));
+    MGB_CUDA(cudaMemsetAsync(d_norm2, 0, 8 * sizeof(double), stream));
+    MGB_CUDA(cudaMalloc(&d_coarse_iters, sizeof(int)));
+    MGB_CUDA(cudaMallocHost(&h_norm2, 8 * sizeof(double)));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    return MGB200_OK;
+}
+
+// Coarse velocity towers (timestepper prologue, multigrid.cpp:148-160).
+int mgb200_solver::build_towers()
+{
+    if (maxlvl == 1) return MGB200_OK;
+    if (opt.correct_towers) {
+        for (int l = 1; l < maxlvl; ++l) {
+            MGB_TRY(launch_restrict(lv[l].v1, lv[l].L, lv[l - 1].v1, lv[l - 1].L, lv[l - 1].n, stream));
+            MGB_TRY(launch_restrict(lv[l].v2, lv[l].L, lv[l - 1].v2, lv[l - 1].L, lv[l - 1].n, stream));
+        }
+        return MGB200_OK;
+    }
+    // Reference-compatible: every level is restriction(dst, src, N/2) on flat zero-filled
+    // (N/2+1)^2 buffers, read back with the level's true stride.
+    const long h = N / 2;
+    const size_t fb = (size_t)(h + 1) * (h + 1) * sizeof(double);
+    for (int k = 0; k < 2; ++k)
+        if (!d_flat[k]) MGB_CUDA(cudaMalloc(&d_flat[k], fb));
+    for (int which = 0; which < 2; ++which) {
+        const double* src0 = which == 0 ? lv[0].v1 : lv[0].v2;
+        int cur = 0;
+        for (int l = 1; l < maxlvl; ++l) {
+            MGB_CUDA(cudaMemsetAsync(d_flat[cur], 0, fb, stream));
+            if (l == 1) MGB_TRY(launch_tower_flat(d_flat[cur], src0, true, lv[0].L, N, stream));
+            else MGB_TRY(launch_tower_flat(d_flat[cur], d_flat[1 - cur], false, lv[0].L, N, stream));
+            double* dst = which == 0 ? lv[l].v1 : lv[l].v2;
+            MGB_TRY(launch_flat_to_level(dst, lv[l].L, d_flat[cur], lv[l].n, stream));
+            cur = 1 - cur;
+        }
+    }
+    return MGB200_OK;
+}
+
+// `iters` RB-GS iterations on the current iterate (unfused: two colour launches each)
+int mgb200_solver::smooth(Level& g, int iters)
+{
+    for (int it = 0; it < iters; ++it) {
+        MGB_TRY(launch_gs_colour(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, 0, opt.arith, stream));
+        MGB_TRY(launch_gs_colour(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, 1, opt.arith, stream));
+    }
+    return MGB200_OK;
+}
+
+// mg_inner (multigrid.cpp:17-92)
+int mgb200_solver::cycle_body(int l)
+{
+    Level& g = lv[l];
+    for (int rep = 0; rep < opt.shape; ++rep) {                                   // multigrid.cpp:52
+        if (l == maxlvl - 1) {
+            // coarsest level: on-device loop {GS; residual; norm} (multigrid.cpp:55-65).  A level
+            // entered from above starts from u = 0 (multigrid.cpp:77); the kernel zero-fills itself.
+            const bool fresh = (l > 0 && rep == 0);
+            MGB_TRY(launch_coarse_solve(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, fresh,
+                                        opt.coarse_maxit, opt.coarse_tol, d_coarse_iters, stream));
+            continue;
+        }
+        Level& c = lv[l + 1];
+        if (opt.plan == MGB200_PLAN_UNFUSED) {
+            MGB_TRY(smooth(g, opt.niter));                                        // :69-72
+            double* tmp = g.u[1 - g.cur];                                         // the idle twin is the scratch
+            MGB_TRY(launch_residual(tmp, g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, nullptr, stream)); // :73
+            MGB_TRY(launch_restrict_interior(c.rhs, c.L, tmp, g.L, g.n, stream)); // :75
+            if (l + 1 != maxlvl - 1)                                              // :77 (coarsest zero-fills itself)
+                MGB_CUDA(cudaMemsetAsync(c.u[c.cur], 0, c.elems * sizeof(double), stream));
+            MGB_TRY(cycle_body(l + 1));                                           // :79
+            MGB_TRY(launch_prolong(g.u[g.cur], g.L, c.u[c.cur], c.L, c.n, true, stream)); // :81-83
+            MGB_TRY(smooth(g, opt.niter));                                        // :85-88
+        } else {
+            // ---- down leg: niter RB iterations, residual, injection: one streaming launch ----
+            const bool zero_in = (l > 0 && rep == 0);     // fresh coarse level: u == 0, nothing to read
+            int left = opt.niter;
+            bool first = true;
+            do {
+                const int k = left > 3 ? 3 : left;
+                left -= k;
+                StreamPassArgs a{};
+                a.n = g.n; a.L = g.L; a.st = g.st; a.arith = opt.arith;
+                a.u_in = (first && zero_in) ? nullptr : g.u[g.cur];
+                a.u_out = g.u[1 - g.cur];
+                a.rhs = g.rhs; a.v1 = g.v1; a.v2 = g.v2;
+                a.iters = k;
+                a.Lc = c.L;
+                if (left == 0) { a.post = POST_INJECT; a.coarse_rhs = c.rhs; }
+                MGB_TRY(stream_pass(a, stream));
+                g.cur = 1 - g.cur;
+                first = false;
+            } while (left > 0);
+            MGB_TRY(cycle_body(l + 1));
+            // ---- up leg: prolong + correct, niter RB iterations (+ residual norm on level 0) ----
+            left = opt.niter;
+            first = true;
+            do {
+                const int k = left > 3 ? 3 : left;
+                left -= k;
+                StreamPassArgs a{};
+                a.n = g.n; a.L = g.L; a.st = g.st; a.arith = opt.arith;
+                a.u_in = g.u[g.cur];
+                a.u_out = g.u[1 - g.cur];
+                a.rhs = g.rhs; a.v1 = g.v1; a.v2 = g.v2;
+                a.iters = k;
+                a.Lc = c.L;
+                if (first) a.coarse_u = c.u[c.cur];
+                if (left == 0 && l == 0 && rep == opt.shape - 1) { a.post = POST_NORM2; a.partials = d_partials; }
+                MGB_TRY(stream_pass(a, stream));
+                g.cur = 1 - g.cur;
+                first = false;
+            } while (left > 0);
+        }
+    }
+    return MGB200_OK;
+}
+
+// residual ; compute_norm on level 0 (multigrid.cpp:112-113) -> d_norm2[0]
+int mgb200_solver::residual_norm_level0()
+{
+    Level& g = lv[0];
+    MGB_TRY(launch_residual(nullptr, g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream));
+    MGB_TRY(launch_reduce_partials(d_partials, residual_partials_count(g.n), d_norm2, stream));
+    return MGB200_OK;
+}
+
+int mgb200_solver::record_cycle()
+{
+    MGB_TRY(cycle_body(0));
+    if (opt.plan == MGB200_PLAN_FUSED && maxlvl > 1) {
+        // the level-0 up leg already produced the per-tile sums of squares
+        MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N), d_norm2, stream));
+    } else {
+        MGB_TRY(residual_norm_level0());
+    }
+    return MGB200_OK;
+}
+
+int mgb200_solver::run_cycle_async()
+{
+    if (!have_rhs) return fail(MGB200_ERR_STATE, "cycle before form_rhs");
+    if (!opt.use_graph) {
+        const long before = launch_counter();
+        MGB_TRY(record_cycle());
+        count(before);
+        return MGB200_OK;
+    }
+    if (!graph_exec) {
+        // every level's `cur` returns to its starting value after one cycle (two flips per
+        // level per repetition), so one captured graph is valid for every later cycle
+        std::vector<int> cur0;
+        for (auto& g : lv) cur0.push_back(g.cur);
+        cudaGraph_t graph = nullptr;
+        const long before = launch_counter();
+        MGB_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = record_cycle();
+        cudaError_t e = cudaStreamEndCapture(stream, &graph);
+        graph_kernels = launch_counter() - before;
+        launch_counter() = before;      // captured, not launched
+        if (rc != MGB200_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(MGB200_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        for (size_t l = 0; l < lv.size(); ++l)
+            if (lv[l].cur != cur0[l]) { cudaGraphDestroy(graph); return fail(MGB200_ERR_STATE, "cycle does not restore buffer parity"); }
+        e = cudaGraphInstantiate(&graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(MGB200_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    MGB_CUDA(cudaGraphLaunch(graph_exec, stream));
+    launches += graph_kernels;
+    return MGB200_OK;
+}
+
+int mgb200_solver::read_norm(double* out)
+{
+    MGB_CUDA(cudaMemcpyAsync(h_norm2, d_norm2, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    res = std::sqrt(h_norm2[0]);                                                  // gs.cpp:106
+    if (out) *out = res;
+    return MGB200_OK;
+}
+
+// compute_rhs (multigrid.cpp:167) fused with the initial residual norm (multigrid.cpp:104-105)
+int mgb200_solver::form_rhs(double* res0_out)
+{
+    if (!have_fields) return fail(MGB200_ERR_STATE, "form_rhs before set_fields");
+    Level& g = lv[0];
+    const long before = launch_counter();
+    MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream));
+    MGB_TRY(launch_reduce_partials(d_partials, residual_partials_count(g.n), d_norm2, stream));
+    count(before);
+    have_rhs = true;
+    MGB_TRY(read_norm(&res0));
+    if (res0_out) *res0_out = res0;
+    return MGB200_OK;
+}
+
+// mg_outer (multigrid.cpp:97-120)
+int mgb200_solver::solve(mgb200_solve_info* info)
+{
+    if (!have_rhs) return fail(MGB200_ERR_STATE, "solve before form_rhs");
+    double r0 = res0, r = res0;
+    int it = 0;
+    if (info) { std::memset(info, 0, sizeof(*info)); info->hist[0] = r0; }
+    for (; it < opt.max_cycle && r / r0 > tol; ++it) {                            // :108
+        MGB_TRY(run_cycle_async());                                               // :110-112
+        MGB_TRY(read_norm(&r));                                                   // :113
+        if (info) info->hist[it + 1] = r;
+    }
+    if (info) { info->cycles = it; info->res0 = r0; info->res = r; info->converged = (r / r0 <= tol) ? 1 : 0; }
+    return MGB200_OK;
+}
+
+int mgb200_solver::get_u_natural(double* dst_dev, long ld)
+{
+    Level& g = lv[0];
+    const long before = launch_counter();
+    MGB_TRY(launch_convert(dst_dev, natural_layout(ld), g.u[g.cur], g.L, g.n, stream));
+    count(before);
+    return MGB200_OK;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int mgb200_version(void) { return MGB200_VERSION; }
+const char* mgb200_last_error(void) { return g_last_error.c_str(); }
+
+void mgb200_default_options(mgb200_options* o)
+{
+    std::memset(o, 0, sizeof(*o));
+    o->struct_size = (int)sizeof(mgb200_options);
+    o->shape = 1;
+    o->niter = 3;
+    o->coarse_maxit = 1000;
+    o->coarse_tol = 1e-5;
+    o->max_cycle = 50;
+    o->arith = MGB200_ARITH_FAST;
+    o->plan = MGB200_PLAN_FUSED;
+    o->correct_towers = 0;
+    o->use_graph = 1;
+    o->device = -1;
+}
+
+int mgb200_create(mgb200_solver** out, long n, int maxlvl, double nu, double dt, double dx, double tol,
+                  const mgb200_options* opt)
+{
+    if (!out) return fail(MGB200_ERR_INVALID, "out == NULL");
+    *out = nullptr;
+    mgb200_solver* s = new mgb200_solver();
+    int rc = s->init(n, maxlvl, nu, dt, dx, tol, opt);
+    if (rc != MGB200_OK) { delete s; return rc; }
+    *out = s;
+    return MGB200_OK;
+}
+
+int mgb200_destroy(mgb200_solver* s)
+{
+    if (!s) return MGB200_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    delete s;
+    return MGB200_OK;
+}
+
+static int after_fields(mgb200_solver* s)
+{
+    MGB_TRY(s->build_towers());
+    s->have_fields = true;
+    s->have_rhs = false;
+    return MGB200_OK;
+}
+
+int mgb200_set_fields_device(mgb200_solver* s, const double* u0, const double* v1, const double* v2, long ld)
+{
+    if (!s || !u0 || !v1 || !v2 || ld < s->N + 1) return fail(MGB200_ERR_INVALID, "set_fields_device: bad argument");
+    Level& g = s->lv[0];
+    const long before = launch_counter();
+    MGB_TRY(launch_convert(g.u[g.cur], g.L, u0, natural_layout(ld), g.n, s->stream));
+    MGB_TRY(launch_convert(g.v1, g.L, v1, natural_layout(ld), g.n, s->stream));
+    MGB_TRY(launch_convert(g.v2, g.L, v2, natural_layout(ld), g.n, s->stream));
+    MGB_TRY(after_fields(s));
+    s->count(before);
+    MGB_CUDA(cudaStreamSynchronize(s->stream));     // the caller may free its arrays on return
+    return MGB200_OK;
+}
+
+int mgb200_set_fields_host(mgb200_solver* s, const double* u0, const double* v1, const double* v2)
+{
+    if (!s || !u0 || !v1 || !v2) return fail(MGB200_ERR_INVALID, "set_fields_host: bad argument");
+    Level& g = s->lv[0];
+    const long n = g.n;
+    const size_t bytes = (size_t)(n + 1) * (n + 1) * sizeof(double);
+    const Layout dense = natural_layout(n + 1);
+    // two staging areas (both larger than a dense field): the idle twin of u and the rhs array
+    double* stage_a = g.u[1 - g.cur];
+    double* stage_b = g.rhs;
+    const long before = launch_counter();
+    MGB_CUDA(cudaMemcpyAsync(stage_a, u0, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.u[g.cur], g.L, stage_a, dense, n, s->stream));
+    MGB_CUDA(cudaMemcpyAsync(stage_b, v1, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.v1, g.L, stage_b, dense, n, s->stream));
+    MGB_CUDA(cudaMemcpyAsync(stage_a, v2, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.v2, g.L, stage_a, dense, n, s->stream));
+    MGB_CUDA(cudaMemsetAsync(stage_a, 0, g.elems * sizeof(double), s->stream));
+    MGB_CUDA(cudaMemsetAsync(stage_b, 0, g.elems * sizeof(double), s->stream));
+    MGB_TRY(after_fields(s));
+    s->count(before);
+    MGB_CUDA(cudaStreamSynchronize(s->stream));
+    return MGB200_OK;
+}
+
+int mgb200_set_fields_reference_ic(mgb200_solver* s, double vscale)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    Level& g = s->lv[0];
+    const long before = launch_counter();
+    MGB_TRY(launch_initial_conditions(g.u[g.cur], g.v1, g.v2, g.n, g.L, vscale, s->stream));
+    MGB_TRY(after_fields(s));
+    s->count(before);
+    return MGB200_OK;
+}
+
+int mgb200_form_rhs(mgb200_solver* s, double* res0)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    return s->form_rhs(res0);
+}
+
+int mgb200_cycle(mgb200_solver* s, double* res)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    MGB_TRY(s->run_cycle_async());
+    return s->read_norm(res);
+}
+
+int mgb200_cycle_async(mgb200_solver* s)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    return s->run_cycle_async();
+}
+
+int mgb200_last_norm(mgb200_solver* s, double* res)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    return s->read_norm(res);
+}
+
+int mgb200_solve(mgb200_solver* s, mgb200_solve_info* info)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    return s->solve(info);
+}
+
+int mgb200_timestep(mgb200_solver* s, int nsteps, mgb200_solve_info* infos)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    for (int k = 0; k < nsteps; ++k) {                                            // multigrid.cpp:165
+        MGB_TRY(s->form_rhs(nullptr));                                            // :167
+        MGB_TRY(s->solve(infos ? &infos[k] : nullptr));                           // :169
+    }
+    return MGB200_OK;
+}
+
+int mgb200_get_u_device(mgb200_solver* s, double* u, long ld)
+{
+    if (!s || !u || ld < s->N + 1) return fail(MGB200_ERR_INVALID, "get_u_device: bad argument");
+    MGB_TRY(s->get_u_natural(u, ld));
+    MGB_CUDA(cudaStreamSynchronize(s->stream));
+    return MGB200_OK;
+}
+
+int mgb200_get_u_host(mgb200_solver* s, double* u)
+{
+    if (!s || !u) return fail(MGB200_ERR_INVALID, "get_u_host: bad argument");
+    Level& g = s->lv[0];
+    double* stage = g.u[1 - g.cur];      // idle between passes
+    MGB_TRY(s->get_u_natural(stage, g.n + 1));
+    MGB_CUDA(cudaMemcpyAsync(u, stage, (size_t)(g.n + 1) * (g.n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    MGB_CUDA(cudaStreamSynchronize(s->stream));
+    return MGB200_OK;
+}
+
+int mgb200_get_level_host(mgb200_solver* s, int lvl, int which, double* out)
+{
+    if (!s || !out || lvl < 0 || lvl >= s->maxlvl || which < 0 || which > 3) return fail(MGB200_ERR_INVALID, "get_level_host: bad argument");
+    Level& g = s->lv[lvl];
+    const double* src = which == 0 ? g.u[g.cur] : which == 1 ? g.rhs : which == 2 ? g.v1 : g.v2;
+    double* tmp = nullptr;
+    const size_t bytes = (size_t)(g.n + 1) * (g.n + 1) * sizeof(double);
+    MGB_CUDA(cudaMalloc(&tmp, bytes));
+    int rc = launch_convert(tmp, natural_layout(g.n + 1), src, g.L, g.n, s->stream);
+    if (rc == MGB200_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(MGB200_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+int mgb200_synchronize(mgb200_solver* s)
+{
+    if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
+    MGB_CUDA(cudaStreamSynchronize(s->stream));
+    return MGB200_OK;
+}
+
+void* mgb200_stream(mgb200_solver* s) { return s ? (void*)s->stream : nullptr; }
+long mgb200_kernel_launches(mgb200_solver* s) { return s ? s->launches : 0; }
+
+// DESIGN.md "bytes model": 8 B per node for every level-sized array a pass reads or writes,
+// 2 B per fine node for an array of the next coarser level.
+double mgb200_cycle_bytes(mgb200_solver* s)
+{
+    if (!s) return 0.0;
+    double total = 0.0;
+    for (int l = 0; l < s->maxlvl; ++l) {
+        const double m = (double)(s->lv[l].n + 1) * (double)(s->lv[l].n + 1);
+        const int reps = 1;   // shape repetitions multiply every coarser level
+        double per_node;
+        if (l == s->maxlvl - 1) {
+            per_node = 40.0;  // one read of u,rhs,v1,v2 + one write of u; iterations stay on chip
+        } else if (s->opt.plan == MGB200_PLAN_UNFUSED) {
+            per_node = 2.0 * s->opt.niter * 40.0 + 40.0 + 4.0 + 2.0 + 26.0;   // GS pre/post, residual, inject, zero, prolong+add
+        } else {
+            const int chunks = s->opt.niter <= 3 ? 1 : (s->opt.niter + 2) / 3;
+            const double down = (l > 0 ? 32.0 : 40.0) + 2.0 + (chunks - 1) * 40.0;  // u,rhs,v1,v2 in (u skipped when zero) + u out + coarse rhs
+            const double up = 40.0 + 2.0 + (chunks - 1) * 40.0;                     // + coarse u in
+            per_node = down + up;
+        }
+        double mult = 1.0;
+        for (int k = 0; k < l; ++k) mult *= s->opt.shape;
+        total += per_node * m * mult * reps;
+    }
+    if (s->opt.plan == MGB200_PLAN_UNFUSED || s->maxlvl == 1) total += 32.0 * (double)(s->N + 1) * (double)(s->N + 1);
+    return total;
+}
+
+int mgb200_profile_level0(mgb200_solver* s, int reps, double* ms_a, double* bytes_a, double* ms_b, double* bytes_b)
+{
+    if (!s || reps < 1 || !s->have_rhs) return fail(MGB200_ERR_STATE, "profile_level0: needs a formed rhs");
+    if (s->maxlvl < 2) return fail(MGB200_ERR_INVALID, "profile_level0: needs at least two levels");
+    Level& g = s->lv[0];
+    Level& c = s->lv[1];
+    const double m0 = (double)(g.n + 1) * (double)(g.n + 1);
+    cudaEvent_t e0, e1;
+    MGB_CUDA(cudaEventCreate(&e0));
+    MGB_CUDA(cudaEventCreate(&e1));
+    double acc[2] = {0.0, 0.0};
+    const long before = launch_counter();
+    int rc = MGB200_OK;
+    for (int which = 0; which < 2 && rc == MGB200_OK; ++which) {
+        for (int r = 0; r < reps && rc == MGB200_OK; ++r) {
+            cudaEventRecord(e0, s->stream);
+            if (s->opt.plan == MGB200_PLAN_FUSED) {
+                StreamPassArgs a{};
+                a.n = g.n; a.L = g.L; a.st = g.st; a.arith = s->opt.arith;
+                a.u_in = g.u[g.cur]; a.u_out = g.u[1 - g.cur];
+                a.rhs = g.rhs; a.v1 = g.v1; a.v2 = g.v2;
+                a.iters = s->opt.niter > 3 ? 3 : s->opt.niter;
+                a.Lc = c.L;
+                if (which == 0) { a.post = POST_INJECT; a.coarse_rhs = c.rhs; }
+                else { a.coarse_u = c.u[c.cur]; a.post = POST_NORM2; a.partials = s->d_partials; }
+                rc = stream_pass(a, s->stream);
+                g.cur = 1 - g.cur;
+            } else if (which == 0) {
+                rc = launch_gs_colour(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, r & 1, s->opt.arith, s->stream);
+            } else {
+                rc = launch_residual(g.u[1 - g.cur], g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, s->opt.arith, nullptr, s->stream);
+            }
+            cudaEventRecord(e1, s->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            acc[which] += ms;
+        }
+    }
+    s->count(before);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    MGB_TRY(rc);
+    if (ms_a) *ms_a = acc[0] / reps;
+    if (ms_b) *ms_b = acc[1] / reps;
+    const bool fused = s->opt.plan == MGB200_PLAN_FUSED;
+    if (bytes_a) *bytes_a = (fused ? 42.0 : 24.0) * m0;   // fused: u,rhs,v1,v2 in + u out + coarse rhs out; colour: u in, half of rhs,v1,v2 in, half of u out
+    if (bytes_b) *bytes_b = (fused ? 42.0 : 40.0) * m0;   // fused: + coarse u in; residual: u,rhs,v1,v2 in + res out
+    return MGB200_OK;
+}
+
+static int timestepper_common(double* uT, const double* u0, const double* v1, const double* v2, double nu, int maxlvl,
+                              int n, double dt, double T, double dx, double tol, int shape, const mgb200_options* opt,
+                              mgb200_solve_info* last, bool host)
+{
+    mgb200_options o;
+    if (opt) o = *opt; else mgb200_default_options(&o);
+    o.shape = shape;
+    mgb200_solver* s = nullptr;
+    MGB_TRY(mgb200_create(&s, n, maxlvl, nu, dt, dx, tol, &o));
+    int rc = host ? mgb200_set_fields_host(s, u0, v1, v2) : mgb200_set_fields_device(s, u0, v1, v2, n + 1);
+    const int nsteps = (int)(T / dt);                                             // multigrid.cpp:165
+    mgb200_solve_info info;
+    std::memset(&info, 0, sizeof(info));
+    for (int k = 0; rc == MGB200_OK && k < nsteps; ++k) {
+        rc = s->form_rhs(nullptr);
+        if (rc == MGB200_OK) rc = s->solve(&info);
+    }
+    if (rc == MGB200_OK) rc = host ? mgb200_get_u_host(s, uT) : mgb200_get_u_device(s, uT, n + 1);   // :175
+    if (last) *last = info;
+    mgb200_destroy(s);
+    return rc;
+}
+
+int mgb200_timestepper_host(double* uT, const double* u0, const double* v1, const double* v2, double nu, int maxlvl,
+                            int n, double dt, double T, double dx, double tol, int shape, const mgb200_options* opt,
+                            mgb200_solve_info* last)
+{
+    if (!uT || !u0 || !v1 || !v2) return fail(MGB200_ERR_INVALID, "timestepper: NULL array");
+    return timestepper_common(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape, opt, last, true);
+}
+
+int mgb200_timestepper_device(double* uT, const double* u0, const double* v1, const double* v2, double nu, int maxlvl,
+                              int n, double dt, double T, double dx, double tol, int shape, const mgb200_options* opt,
+                              mgb200_solve_info* last)
+{
+    if (!uT || !u0 || !v1 || !v2) return fail(MGB200_ERR_INVALID, "timestepper: NULL array");
+    return timestepper_common(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape, opt, last, false);
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// stream_pass.cuh -- interface of the fused streaming kernel (definition: stream_pass.cu).
+//
+// One launch = one "pass" over one level in the solver's split layout:
+//     [u += P(coarse u)]  ->  K red-black Gauss-Seidel iterations  ->  [residual epilogue]
+// read once from HBM, written once (out-of-place: in != out, so tiles never see each other's
+// results), the whole chain staged through shared memory by bulk (TMA) copies.
+#pragma once
+#include "common.cuh"
+
+namespace mgb200 {
+
+enum StreamPost {
+    POST_NONE = 0,
+    POST_INJECT = 1,   // coarse_rhs[I][J] = residual(2I,2J) on the coarse interior (residual ; restriction)
+    POST_NORM2 = 2     // sum of squares of the residual over the interior -> partials (residual ; compute_norm)
+};
+
+struct StreamPassArgs {
+    long n;                 // this level's n (even)
+    Layout L;               // split layout of this level
+    Stencil st;
+    const double* u_in;     // may be null: u is identically zero on entry (fresh coarse level)
+    double* u_out;          // != u_in
+    const double* rhs;
+    const double* v1;
+    const double* v2;
+    int iters;              // K in [0,3]
+    // optional prologue: u += P(coarse)
+    const double* coarse_u; // null = none
+    Layout Lc;              // layout of the (n/2) level
+    // optional epilogue
+    int post;               // StreamPost
+    double* coarse_rhs;     // POST_INJECT target (layout Lc)
+    double* partials;       // POST_NORM2: one double per tile, stream_pass_tiles() entries
+    int arith;
+};
+
+// number of tiles (= partial sums) a pass over level n uses
+long stream_pass_tiles(long n);
+// one-time attribute setup
+int stream_pass_init();
+int stream_pass(const StreamPassArgs& a, cudaStream_t s);
+
+}  // namespace mgb200
