@@ -1,0 +1,117 @@
+// sp_emu.cpp -- TEST INFRASTRUCTURE: a host emulation of the fused streaming kernel.
+//
+// There is no GPU in the build container, so the index logic of the streaming pass (ring slots,
+// pipeline lags, halo validity, split-layout clipping) is exercised here by compiling the very
+// same per-thread step code (csrc/stream_pass_body.cuh) for the host and running the threads of a
+// block one after another inside each step.  Asynchronous primitives become immediate memcpy;
+// shared memory starts as NaN so that any read of a cell that was never staged poisons the
+// result.  Thread order inside a step is selectable (ascending / descending / shuffled): a result
+// that depends on it reveals an intra-step race.  Never linked into libmgb200.so.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <vector>
+
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __shfl_down_sync(unsigned, double v, int) { return v; }
+static inline void __syncthreads() {}
+#define SP_FN static inline
+#include <cuda_runtime.h>
+static uint3 threadIdx, blockDim;
+#include "../../hpcclassmultigridproject_b200/csrc/stream_pass_body.cuh"
+
+namespace mgb200 {
+void set_error(const std::string&) {}
+int fail(int code, const std::string&) { return code; }
+long& launch_counter() { static long c = 0; return c; }
+namespace sp {
+SP_FN void sp_bar_expect(unsigned long long*, unsigned) {}
+SP_FN void sp_bulk_load(double* sdst, const double* gsrc, unsigned bytes, unsigned long long*) { std::memcpy(sdst, gsrc, bytes); }
+SP_FN void sp_bar_wait(unsigned long long*, unsigned) {}
+SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes) { std::memcpy(gdst, ssrc, bytes); }
+SP_FN void sp_store_commit() {}
+SP_FN void sp_store_wait_read2() {}
+SP_FN void sp_fence_async() {}
+}  // namespace sp
+}  // namespace mgb200
+
+using namespace mgb200;
+using namespace mgb200::sp;
+
+extern "C" {
+
+// Runs one pass over level n on HOST arrays in the split layout.  wk/nbands <= 0: use the planner.
+// order: 0 ascending thread ids, 1 descending, 2 shuffled per step.  partials: >= ntiles doubles.
+// Returns the number of tiles, or -1 on a bad argument.
+long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const double* u_in, double* u_out,
+                const double* rhs, const double* v1, const double* v2, const double* cu, double* crhs,
+                double* partials, int K, int post, int arith, double dt, double nu, double dx, int wk, int nbands,
+                int order)
+{
+    if (K < 0 || K > KMAX || n < 8 || (n & 3)) return -1;
+    Params p{};
+    p.n = n; p.nhalf = n / 2; p.pitch = pitch; p.odd = odd; p.cpitch = cpitch; p.codd = codd;
+    Plan pl = make_plan(n, K, 148);
+    if (wk > 0) {
+        pl.WK = wk; pl.SWK = wk + 2 * HK; pl.nstrips = (int)((n / 2 + 1 + wk - 1) / wk);
+    }
+    if (nbands > 0) {
+        pl.RBAND = (n + 1 + nbands - 1) / nbands; pl.nbands = (int)((n + 1 + pl.RBAND - 1) / pl.RBAND);
+    }
+    if (pl.SWK > SWK_MAX || (pl.WK & 3)) return -1;
+    p.RBAND = pl.RBAND; p.WK = pl.WK; p.SWK = pl.SWK; p.nstrips = pl.nstrips; p.nbands = pl.nbands;
+    p.K = K; p.pre = cu ? 1 : 0; p.post = post; p.write_u = (K > 0 || cu) ? 1 : 0; p.u_is_zero = u_in ? 0 : 1;
+    // Stencil exactly as make_stencil (solver.cu)
+    {
+        volatile double r = 0.5 * dt / (dx * dx);
+        volatile double four_r = 4.0 * r;
+        volatile double four_r_nu = four_r * nu;
+        p.st.r = r; p.st.nu = nu; p.st.h = dx; p.st.diag = 1.0 - four_r_nu; p.st.diag_rhs = 1.0 + four_r_nu;
+        p.st.inv_diag = 1.0 / p.st.diag; p.st.hr = r * dx * 0.5; p.st.rnu = r * nu;
+    }
+    std::vector<double> zero(4 * SWK_MAX, 0.0);
+    p.u_in = u_in; p.rhs = rhs; p.v1 = v1; p.v2 = v2; p.cu = cu; p.zero_row = zero.data();
+    p.u_out = u_out; p.crhs = crhs; p.partials = partials;
+    const long ntiles = (long)pl.nstrips * pl.nbands;
+    std::vector<unsigned char> smem(SMEM_BYTES);
+    std::vector<int> perm(THREADS);
+    unsigned rng = 12345u;
+    for (long tile = 0; tile < ntiles; ++tile) {
+        double* sd = reinterpret_cast<double*>(smem.data());
+        for (size_t q = 0; q < SMEM_BYTES / 8; ++q) sd[q] = std::numeric_limits<double>::quiet_NaN();
+        Smem sm;
+        carve(sm, smem.data());
+        const Tile tl = make_tile(p, tile);
+        producer_prologue(p, tl, sm);
+        std::vector<double> acc(THREADS, 0.0);
+        const long t1 = last_step(p, tl);
+        for (long t = first_step(tl); t <= t1; ++t) {
+            std::iota(perm.begin(), perm.end(), 0);
+            if (order == 1) std::reverse(perm.begin(), perm.end());
+            if (order == 2)
+                for (int a = THREADS - 1; a > 0; --a) {
+                    rng = rng * 1664525u + 1013904223u;
+                    std::swap(perm[a], perm[(rng >> 8) % (a + 1)]);
+                }
+            for (int q = 0; q < THREADS; ++q) {
+                const int tid = perm[q];
+                if (arith == MGB200_ARITH_EXACT) thread_step<MGB200_ARITH_EXACT>(p, tl, sm, t, tid, acc[tid]);
+                else thread_step<MGB200_ARITH_FAST>(p, tl, sm, t, tid, acc[tid]);
+            }
+        }
+        if (post == POST_NORM2) {
+            double s = 0.0;
+            for (double a : acc) s += a;
+            partials[tile] = s;
+        }
+    }
+    return ntiles;
+}
+
+}  // extern "C"
