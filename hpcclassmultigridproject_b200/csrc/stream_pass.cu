@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     Smem sm;
     carve(sm, smem_raw);
     const Tile tl = make_tile(p, blockIdx.x);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < RING; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.full[s])) : "memory");
@@ -65,15 +65,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     }
     __syncthreads();
     if (tid == PRODUCER_WARP * 32) producer_prologue(p, tl, sm);
-    double acc = 0.0;
-    const long t1 = last_step(p, tl);
-    for (long t = first_step(tl); t <= t1; ++t) {
-        thread_step<ARITH>(p, tl, sm, t, tid, acc);
+    ThreadState st = init_thread(p, tl, tid);
+    wait_first_row(sm);
+    const int t1 = last_step(p, tl);
+    for (int t = first_step(tl); t <= t1; ++t) {
+        thread_step<ARITH>(p, tl, sm, st, t, lane);
         __syncthreads();
     }
     if (tid == PRODUCER_WARP * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.post == POST_NORM2) {
-        const double tot = block_sum(acc, scratch);
+        const double tot = block_sum(st.acc, scratch);
         if (tid == 0) p.partials[blockIdx.x] = tot;
     }
 }
@@ -111,8 +112,12 @@ int stream_pass_init()
     return MGB200_OK;
 }
 
-long stream_pass_tiles(long n)
+long stream_pass_tiles(long n, int iters)
 {
+    if (iters >= 0) {
+        const Plan& pl = plan_for(n, iters > KMAX ? KMAX : iters);
+        return (long)pl.nstrips * pl.nbands;
+    }
     long m = 0;
     for (int K = 0; K <= KMAX; ++K) {
         const Plan& pl = plan_for(n, K);

@@ -35,8 +35,9 @@ struct StreamPassArgs {
     int arith;
 };
 
-// number of tiles (= partial sums) a pass over level n uses
-long stream_pass_tiles(long n);
+// number of tiles (= partial sums written by POST_NORM2) of a pass over level n with `iters`
+// fused iterations; iters < 0: the maximum over all iteration counts (buffer sizing)
+long stream_pass_tiles(long n, int iters);
 // one-time attribute setup
 int stream_pass_init();
 int stream_pass(const StreamPassArgs& a, cudaStream_t s);

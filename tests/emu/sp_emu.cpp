@@ -89,9 +89,11 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
         carve(sm, smem.data());
         const Tile tl = make_tile(p, tile);
         producer_prologue(p, tl, sm);
-        std::vector<double> acc(THREADS, 0.0);
-        const long t1 = last_step(p, tl);
-        for (long t = first_step(tl); t <= t1; ++t) {
+        std::vector<ThreadState> st(THREADS);
+        for (int tid = 0; tid < THREADS; ++tid) st[tid] = init_thread(p, tl, tid);
+        wait_first_row(sm);
+        const int t1 = last_step(p, tl);
+        for (int t = first_step(tl); t <= t1; ++t) {
             std::iota(perm.begin(), perm.end(), 0);
             if (order == 1) std::reverse(perm.begin(), perm.end());
             if (order == 2)
@@ -101,13 +103,13 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
                 }
             for (int q = 0; q < THREADS; ++q) {
                 const int tid = perm[q];
-                if (arith == MGB200_ARITH_EXACT) thread_step<MGB200_ARITH_EXACT>(p, tl, sm, t, tid, acc[tid]);
-                else thread_step<MGB200_ARITH_FAST>(p, tl, sm, t, tid, acc[tid]);
+                if (arith == MGB200_ARITH_EXACT) thread_step<MGB200_ARITH_EXACT>(p, tl, sm, st[tid], t, tid & 31);
+                else thread_step<MGB200_ARITH_FAST>(p, tl, sm, st[tid], t, tid & 31);
             }
         }
         if (post == POST_NORM2) {
             double s = 0.0;
-            for (double a : acc) s += a;
+            for (const ThreadState& a : st) s += a.acc;
             partials[tile] = s;
         }
     }
