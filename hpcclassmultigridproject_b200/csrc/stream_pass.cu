@@ -1,7 +1,10 @@
 // stream_pass.cu -- device primitives (inline PTX: mbarrier + cp.async.bulk, i.e. the TMA engine
 // in its 1-D bulk form), the kernel, the tile planner and the launcher of the fused streaming pass.
 // The per-thread logic lives in stream_pass_body.cuh.
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstring>
 #include <map>
 #include <mutex>
 
@@ -17,10 +20,18 @@ SP_FN void sp_bar_expect(unsigned long long* bar, unsigned bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-SP_FN void sp_bulk_load(double* sdst, const double* gsrc, unsigned bytes, unsigned long long* bar)
+SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long* bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(sdst)),
+        "l"(&p.maps[which]), "r"(x), "r"(0), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+SP_FN void sp_tma_prefetch(const Params& p, int which, int x, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&p.maps[which]), "r"(x), "r"(0), "r"(z)
                  : "memory");
 }
 
@@ -58,7 +69,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     const Tile tl = make_tile(p, blockIdx.x);
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < RING; ++s)
+        for (int s = 0; s < NGROUP; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.full[s])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sp_fence_async();
@@ -80,7 +91,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
 }
 
 static int g_sms = 0;
-static double* g_zero_row = nullptr;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+// {run, parity, row} view of a split-layout field: dim0 = pairs of one run (stride 8 B, extent = the
+// run stride `odd`, slack included), dim1 = parity (stride odd*8), dim2 = rows (stride pitch*8).
+static int encode_field(TensorMapStorage* out, const double* base, long odd, long pitch, long rows, int box_x, int box_rows)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapStorage), "CUtensorMap size");
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)odd, 2, (cuuint64_t)rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)odd * 8, (cuuint64_t)pitch * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)box_x, 2, (cuuint32_t)box_rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MGB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    std::memcpy(out, &m, sizeof(m));
+    return MGB200_OK;
+}
 
 static const Plan& plan_for(long n, int K)
 {
@@ -106,8 +139,11 @@ int stream_pass_init()
     MGB_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     MGB_CUDA(cudaFuncSetAttribute(k_stream_pass<MGB200_ARITH_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     MGB_CUDA(cudaFuncSetAttribute(k_stream_pass<MGB200_ARITH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MGB_CUDA(cudaMalloc(&g_zero_row, 4 * SWK_MAX * sizeof(double)));
-    MGB_CUDA(cudaMemset(g_zero_row, 0, 4 * SWK_MAX * sizeof(double)));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(MGB200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = (EncodeTiledFn)fn;
     done = true;
     return MGB200_OK;
 }
@@ -143,8 +179,15 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
     p.post = a.post;
     p.write_u = (a.iters > 0 || a.coarse_u) ? 1 : 0;
     p.u_is_zero = a.u_in ? 0 : 1;
+    p.CW = pl.SWK / 2 + 8;
     p.st = a.st;
-    p.u_in = a.u_in; p.rhs = a.rhs; p.v1 = a.v1; p.v2 = a.v2; p.cu = a.coarse_u; p.zero_row = g_zero_row;
+    p.u_in = a.u_in; p.rhs = a.rhs; p.v1 = a.v1; p.v2 = a.v2; p.cu = a.coarse_u;
+    // the u map of a zero-input pass is never dereferenced (its boxes lie out of bounds): any valid field will do
+    MGB_TRY(encode_field(&p.maps[FIELD_U], a.u_in ? a.u_in : a.rhs, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_F], a.rhs, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_V1], a.v1, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_V2], a.v2, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
+    if (a.coarse_u) MGB_TRY(encode_field(&p.maps[FIELD_C], a.coarse_u, a.Lc.odd, a.Lc.pitch, a.n / 2 + 1, p.CW, CROWS));
     p.u_out = a.u_out; p.crhs = a.coarse_rhs; p.partials = a.partials;
     if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "stream_pass: POST_INJECT without coarse_rhs");
     if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "stream_pass: POST_NORM2 without partials");

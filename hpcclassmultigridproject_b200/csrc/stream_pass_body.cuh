@@ -19,6 +19,10 @@
 // TMA engine).  Per-thread state that advances by one row per step (ring slots, rows) is kept
 // incrementally, so a step has no division and almost no address arithmetic.
 //
+// Loads are 3-D TMA tensor copies: one instruction brings GROUP rows x both parity runs x SWK pairs
+// of one field ({SWK, 2, GROUP} box of the {run, parity, row} view of the split layout) and
+// zero-fills whatever lies outside the array; five instructions per GROUP rows feed a tile.
+//
 // This header holds no CUDA-specific instruction: everything asynchronous goes through the sp_*
 // primitives declared below, defined with inline PTX in stream_pass.cu (and as plain memcpy in the
 // host emulation used by tests/test_stream_pass_emu.py).
@@ -35,10 +39,12 @@ namespace sp {
 
 constexpr int SWK_MAX = 128;   // pairs (= 2 columns) per shared-memory row
 constexpr int HK = 4;          // halo pairs per strip side (8 columns >= 2K+1 for K <= 3)
-constexpr int RING = 24;       // fine-row ring slots  >= DEPTH + 4K + 4
-constexpr int DEPTH = 8;       // rows in flight ahead of the compute front
-constexpr int CRING = 8;       // coarse-row ring slots
-constexpr int CW = 72;         // doubles per coarse parity run in smem (>= SWK_MAX/2 + 2)
+constexpr int GROUP = 4;       // rows per TMA box
+constexpr int RING = 24;       // fine-row ring slots: rows t-4K-3 .. t in use + one group in flight
+constexpr int NGROUP = RING / GROUP;
+constexpr int LEAD = 5;        // a group is requested LEAD steps before its first row is consumed
+constexpr int CROWS = 3;       // coarse rows travelling with a group of fine rows
+constexpr int CW_MAX = SWK_MAX / 2 + 8;   // doubles per coarse parity run in smem
 constexpr int KMAX = 3;
 constexpr int NSTAGE = 2 * KMAX;
 constexpr int NPRE = 2;        // prolongation warps (64 pairs each)
@@ -47,7 +53,11 @@ constexpr int WARPS = NSTAGE + NPRE + NPOST + 1;
 constexpr int THREADS = WARPS * 32;
 constexpr int PRODUCER_WARP = WARPS - 1;
 
+// opaque storage for a CUtensorMap (128 bytes, 64-byte aligned); filled by the host launcher
+struct alignas(64) TensorMapStorage { unsigned long long q[16]; };
+
 struct Params {
+    TensorMapStorage maps[5];  // Field order: u_in, rhs, v1, v2, coarse u
     long n, nhalf;             // level size, n/2
     long pitch, odd;           // split layout of this level
     long cpitch, codd;         // split layout of the next coarser level
@@ -58,14 +68,14 @@ struct Params {
     int pre;                   // 1: u += P(coarse u) before smoothing
     int post;                  // StreamPost
     int write_u;               // 0 for a pure residual pass
-    int u_is_zero;             // u_in == 0 everywhere: rows come from zero_row
+    int u_is_zero;             // u_in == 0 everywhere: rows are zero-filled by an out-of-bounds box
+    int CW;                    // SWK/2 + 8: coarse pairs per smem run
     Stencil st;
     const double* u_in;
     const double* rhs;
     const double* v1;
     const double* v2;
     const double* cu;          // coarse u (pre)
-    const double* zero_row;    // >= 2*SWK_MAX zeros
     double* u_out;
     double* crhs;              // coarse rhs (POST_INJECT)
     double* partials;          // POST_NORM2
@@ -79,15 +89,17 @@ struct Tile {
 };
 
 struct Smem {
-    double* U;                 // [RING][2][SWK_MAX]
+    double* U;                 // [RING][2][SWK]
     double* F;                 // rhs
     double* V1;
     double* V2;
-    double* C;                 // [CRING][2][CW]
-    unsigned long long* full;  // [RING] load-completion barriers
+    double* C;                 // [NGROUP][CROWS][2][CW]
+    unsigned long long* full;  // [NGROUP] load-completion barriers
 };
 
-constexpr size_t SMEM_BYTES = (size_t)4 * RING * 2 * SWK_MAX * 8 + (size_t)CRING * 2 * CW * 8 + RING * 8 + 128;
+enum Field { FIELD_U = 0, FIELD_F = 1, FIELD_V1 = 2, FIELD_V2 = 3, FIELD_C = 4 };
+
+constexpr size_t SMEM_BYTES = (size_t)4 * RING * 2 * SWK_MAX * 8 + (size_t)NGROUP * CROWS * 2 * CW_MAX * 8 + NGROUP * 8 + 128;
 
 struct alignas(16) D2 { double x, y; };    // 16-byte vector; aligned accesses only (even pair index)
 
@@ -100,7 +112,7 @@ SP_FN void carve(Smem& sm, unsigned char* base)
     double* d = reinterpret_cast<double*>(base);
     sm.U = d; sm.F = d + row; sm.V1 = d + 2 * row; sm.V2 = d + 3 * row;
     sm.C = d + 4 * row;
-    sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)CRING * 2 * CW);
+    sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)NGROUP * CROWS * 2 * CW_MAX);
 }
 
 SP_FN Tile make_tile(const Params& p, long tile)
@@ -121,12 +133,16 @@ SP_FN Tile make_tile(const Params& p, long tile)
 
 SP_FN int wrap_slot(int s) { return s >= RING ? s - RING : (s < 0 ? s + RING : s); }
 SP_FN int ring_slot(const Tile& tl, int row) { return (row - tl.R0) % RING; }
-SP_FN int rowix(int slot, int par) { return (slot * 2 + par) * SWK_MAX; }
+
 
 // ------------------------------------------------------------------------------------------
 // asynchronous primitives
 SP_FN void sp_bar_expect(unsigned long long* bar, unsigned bytes);
-SP_FN void sp_bulk_load(double* sdst, const double* gsrc, unsigned bytes, unsigned long long* bar);
+// 3-D tensor load of field `which`: box {SWK (CW for FIELD_C), 2, GROUP (CROWS)} whose first element
+// is (pair x, parity 0, row z) of the field; out-of-bounds elements arrive as zeros
+SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long* bar);
+// same box, pulled into L2 only (no shared-memory destination)
+SP_FN void sp_tma_prefetch(const Params& p, int which, int x, int z);
 SP_FN void sp_bar_wait(unsigned long long* bar, unsigned parity);
 SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes);
 SP_FN void sp_store_commit();
@@ -134,61 +150,29 @@ SP_FN void sp_store_wait_read2();
 SP_FN void sp_fence_async();
 
 // ------------------------------------------------------------------------------------------
-// producer: bulk loads of fine row r (4 fields x 2 parity runs) and of the coarse rows that
-// travel with it, all completing on full[slot(r)]
-SP_FN void issue_row_loads(const Params& p, const Tile& tl, const Smem& sm, int r)
+// producer: request group g (rows R0+4g .. R0+4g+3) of the four fields, plus the three coarse rows
+// its prolongation needs; everything completes on full[g % NGROUP]
+SP_FN void issue_group_loads(const Params& p, const Tile& tl, const Smem& sm, int g)
 {
-    const int slot = ring_slot(tl, r);
-    unsigned long long* bar = &sm.full[slot];
-    // even run: pairs [k0, k0+SWK) clipped to [0, nhalf+1 rounded up to even); odd run: to [0, nhalf)
-    const long s0 = tl.k0 < 0 ? 0 : tl.k0;
-    long eE = (long)tl.k0 + p.SWK, eO = eE;
-    const long capE = (p.nhalf + 2) & ~1L, capO = p.nhalf;
-    if (eE > capE) eE = capE;
-    if (eO > capO) eO = capO;
-    const long nE = eE > s0 ? eE - s0 : 0, nO = eO > s0 ? eO - s0 : 0;
-    // coarse rows loaded with this fine row: I is first needed by fine row 2I-1
-    long cI[2]; int ncI = 0;
-    if (p.pre) {
-        if (r == tl.R0) {
-            cI[ncI++] = r >> 1;
-            if (r & 1) cI[ncI++] = (r + 1) >> 1;
-        } else if (r & 1) {
-            cI[ncI++] = (r + 1) >> 1;
-        }
-    }
-    const long m0 = tl.k0 / 2;                          // k0 is a multiple of 4 (or -4)
-    const long ms = m0 < 0 ? 0 : m0;
-    long ceE = m0 + p.SWK / 2 + 2, ceO = m0 + p.SWK / 2;
-    const long ccapE = (p.nhalf / 2 + 2) & ~1L, ccapO = p.nhalf / 2;
-    if (ceE > ccapE) ceE = ccapE;
-    if (ceO > ccapO) ceO = ccapO;
-    const long cnE = ceE > ms ? ceE - ms : 0, cnO = ceO > ms ? ceO - ms : 0;
-
-    const unsigned total = (unsigned)(4 * (nE + nO) * 8 + ncI * (cnE + cnO) * 8);
-    sp_bar_expect(bar, total);
-    const long goff = (long)r * p.pitch + s0;
-    const long soff = s0 - tl.k0;
-    const double* usrc = p.u_is_zero ? p.zero_row : p.u_in + goff;
-    const double* usrcO = p.u_is_zero ? p.zero_row : p.u_in + goff + p.odd;
-    if (nE > 0) {
-        sp_bulk_load(sm.U + rowix(slot, 0) + soff, usrc, (unsigned)(nE * 8), bar);
-        sp_bulk_load(sm.F + rowix(slot, 0) + soff, p.rhs + goff, (unsigned)(nE * 8), bar);
-        sp_bulk_load(sm.V1 + rowix(slot, 0) + soff, p.v1 + goff, (unsigned)(nE * 8), bar);
-        sp_bulk_load(sm.V2 + rowix(slot, 0) + soff, p.v2 + goff, (unsigned)(nE * 8), bar);
-    }
-    if (nO > 0) {
-        sp_bulk_load(sm.U + rowix(slot, 1) + soff, usrcO, (unsigned)(nO * 8), bar);
-        sp_bulk_load(sm.F + rowix(slot, 1) + soff, p.rhs + goff + p.odd, (unsigned)(nO * 8), bar);
-        sp_bulk_load(sm.V1 + rowix(slot, 1) + soff, p.v1 + goff + p.odd, (unsigned)(nO * 8), bar);
-        sp_bulk_load(sm.V2 + rowix(slot, 1) + soff, p.v2 + goff + p.odd, (unsigned)(nO * 8), bar);
-    }
-    for (int q = 0; q < ncI; ++q) {
-        const long I = cI[q];
-        const int cs = (int)(I % CRING);
-        const long cg = I * p.cpitch + ms;
-        if (cnE > 0) sp_bulk_load(sm.C + (long)(cs * 2 + 0) * CW + (ms - m0), p.cu + cg, (unsigned)(cnE * 8), bar);
-        if (cnO > 0) sp_bulk_load(sm.C + (long)(cs * 2 + 1) * CW + (ms - m0), p.cu + cg + p.codd, (unsigned)(cnO * 8), bar);
+    const int gs = g % NGROUP;
+    unsigned long long* bar = &sm.full[gs];
+    const int z = tl.R0 + GROUP * g;
+    const unsigned fine = (unsigned)(GROUP * 2 * p.SWK * 8), coarse = (unsigned)(CROWS * 2 * p.CW * 8);
+    sp_bar_expect(bar, 4u * fine + (p.pre ? coarse : 0u));
+    const long so = (long)gs * GROUP * 2 * p.SWK;
+    // a zero iterate is produced by a box that lies entirely below the last row
+    sp_tma_load(p, FIELD_U, sm.U + so, tl.k0, p.u_is_zero ? (int)p.n + 64 : z, bar);
+    sp_tma_load(p, FIELD_F, sm.F + so, tl.k0, z, bar);
+    sp_tma_load(p, FIELD_V1, sm.V1 + so, tl.k0, z, bar);
+    sp_tma_load(p, FIELD_V2, sm.V2 + so, tl.k0, z, bar);
+    if (p.pre) sp_tma_load(p, FIELD_C, sm.C + (long)gs * CROWS * 2 * p.CW, tl.k0 / 2, z >> 1, bar);
+    // start the HBM fetch of the group after next: its shared-memory request will then hit L2
+    const int zp = z + 2 * GROUP;
+    if (zp <= tl.R1) {
+        if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_F, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_V1, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_V2, tl.k0, zp);
     }
 }
 
@@ -203,8 +187,9 @@ SP_FN void issue_row_store(const Params& p, const Tile& tl, const Smem& sm, int 
     const long nE = (eE - tl.kb + 1) & ~1L;             // rounded up to a whole 16-byte unit (layout slack)
     const long nO = eO - tl.kb;
     const long goff = (long)q * p.pitch + tl.kb;
-    if (nE > 0) sp_bulk_store(p.u_out + goff, sm.U + rowix(slot, 0) + lo, (unsigned)(nE * 8));
-    if (nO > 0) sp_bulk_store(p.u_out + goff + p.odd, sm.U + rowix(slot, 1) + lo, (unsigned)(nO * 8));
+    const long so = (long)slot * 2 * p.SWK + lo;
+    if (nE > 0) sp_bulk_store(p.u_out + goff, sm.U + so, (unsigned)(nE * 8));
+    if (nO > 0) sp_bulk_store(p.u_out + goff + p.odd, sm.U + so + p.SWK, (unsigned)(nO * 8));
     sp_store_commit();
 }
 
@@ -217,10 +202,11 @@ struct ThreadState {
     int idx;       // stage number / chunk number
     int kk;        // first local pair handled (stage: also kk + 64)
     int row;       // the role's row at the current step
-    int slot;      // ring slot of that row
+    int base;      // element offset of that row's even run in the ring: slot * 2 * SWK
     unsigned ok;   // validity bits (role specific)
-    int wslot;     // ring slot of the row whose arrival is awaited at the end of the step
-    unsigned wpar; // and its phase parity
+    int wphase;    // (row awaited at the end of the step - R0) mod GROUP
+    int wgroup;    // its group slot
+    unsigned wpar; // and that barrier's phase parity
     double acc;    // POST_NORM2 accumulator
 };
 
@@ -262,10 +248,13 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, int tid)
         s.role = ROLE_PRODUCER; off = 0;
     }
     s.row = tl.R0 - off;
-    s.slot = ((RING - off) % RING + RING) % RING;        // slot of row R0 is 0
-    s.wslot = 0; s.wpar = 0;
+    s.base = (((RING - off) % RING + RING) % RING) * 2 * p.SWK;      // row R0 sits in slot 0
+    s.wphase = 0; s.wgroup = 0; s.wpar = 0;
     return s;
 }
+
+SP_FN int ring_next(const Params& p, int base) { const int b = base + 2 * p.SWK; return b == RING * 2 * p.SWK ? 0 : b; }
+SP_FN int ring_prev(const Params& p, int base) { return (base == 0 ? RING * 2 * p.SWK : base) - 2 * p.SWK; }
 
 // one half-sweep stage on row st.row: colour = stage & 1; two 16-byte vectors per lane
 template <int ARITH>
@@ -275,8 +264,9 @@ SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const Thre
     if (st.idx >= 2 * p.K || i <= tl.R0 || i >= tl.R1) return;      // rows i-1 and i+1 must be staged
     const int par = (st.idx + i) & 1;                                 // column parity of this colour in row i
     const unsigned ok = (st.ok >> (par * 4)) & 15u;
-    const int sc = st.slot, su = wrap_slot(sc - 1), sd = wrap_slot(sc + 1);
-    const int bc = rowix(sc, par), bo = rowix(sc, par ^ 1), bu = rowix(su, par), bd = rowix(sd, par);
+    const int pofs = par ? p.SWK : 0;
+    const int bc = st.base + pofs, bo = st.base + (p.SWK - pofs);     // this parity / the other parity of row i
+    const int bu = ring_prev(p, st.base) + pofs, bd = ring_next(p, st.base) + pofs;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
         const unsigned okg = (ok >> (2 * g)) & 3u;
@@ -305,25 +295,26 @@ SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const Thre
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
-// Coarse column (k0 + kk) sits at local index kk of the coarse ring row: even kk in the E run at
-// kk/2, odd kk in the O run at kk/2.
+// The coarse rows of a group start at coarse row (first fine row of the group) >> 1; coarse column
+// (k0 + kk) sits at local index kk: even kk in the E run at kk/2, odd kk in the O run at kk/2.
 SP_FN void prolong_row(const Params& p, const Tile& tl, const Smem& sm, const ThreadState& st)
 {
     const int t = st.row;
     if (!p.pre || (st.ok & 3u) == 0 || t < 1 || t > p.n - 1 || t < tl.R0 || t > tl.R1) return;
     const int kk = st.kk, a = kk >> 1;                  // kk even
-    const int I = t >> 1;
-    const int c0 = (I % CRING) * 2 * CW, c1 = ((I + 1) % CRING) * 2 * CW;
-    const int be = rowix(st.slot, 0), bo = rowix(st.slot, 1);
+    const int g = (t - tl.R0) / GROUP;
+    const int crow = (t >> 1) - ((tl.R0 + GROUP * g) >> 1);           // 0..1; the row below it is crow+1
+    const int c0 = ((g % NGROUP) * CROWS + crow) * 2 * p.CW, c1 = c0 + 2 * p.CW;
+    const int be = st.base, bo = st.base + p.SWK;
     // coarse columns kk, kk+1, kk+2 of coarse row I (and I+1 for an odd fine row)
-    const double a0 = sm.C[c0 + a], a1 = sm.C[c0 + CW + a], a2 = sm.C[c0 + a + 1];
+    const double a0 = sm.C[c0 + a], a1 = sm.C[c0 + p.CW + a], a2 = sm.C[c0 + a + 1];
     D2 ue = ld2(sm.U + be + kk), uo = ld2(sm.U + bo + kk);
     double e0, e1, o0, o1;
     if ((t & 1) == 0) {
         e0 = a0; e1 = a1;                                                                   // gs.cpp:238
         o0 = __dmul_rn(__dadd_rn(a0, a1), 0.5); o1 = __dmul_rn(__dadd_rn(a1, a2), 0.5);     // gs.cpp:240
     } else {
-        const double b0 = sm.C[c1 + a], b1 = sm.C[c1 + CW + a], b2 = sm.C[c1 + a + 1];
+        const double b0 = sm.C[c1 + a], b1 = sm.C[c1 + p.CW + a], b2 = sm.C[c1 + a + 1];
         e0 = __dmul_rn(__dadd_rn(a0, b0), 0.5); e1 = __dmul_rn(__dadd_rn(a1, b1), 0.5);     // gs.cpp:239
         o0 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a0, b0), a1), b1), 0.25);              // gs.cpp:241
         o1 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a1, b1), a2), b2), 0.25);
@@ -343,13 +334,12 @@ SP_FN void post_row(const Params& p, const Tile& tl, const Smem& sm, ThreadState
     if (p.post == POST_NONE || st.ok == 0 || q < lo || q > hi) return;
     if (p.post == POST_INJECT && (q & 1)) return;
     const int kk = st.kk;
-    const int sc = st.slot, su = wrap_slot(sc - 1), sd = wrap_slot(sc + 1);
-    const int e = rowix(sc, 0) + kk, o = rowix(sc, 1) + kk;
+    const int bu = ring_prev(p, st.base), bd = ring_next(p, st.base);
+    const int e = st.base + kk, o = st.base + p.SWK + kk;
     const double ue = sm.U[e], uo = sm.U[o];
     if (st.ok & 1u) {                                    // even column 2kg
         const Coef4 c = Arith<ARITH>::coef(sm.V1[e], sm.V2[e], p.st);
-        const double rv = Arith<ARITH>::residual(sm.F[e], ue, sm.U[rowix(su, 0) + kk], sm.U[o - 1],
-                                                 sm.U[rowix(sd, 0) + kk], uo, c, p.st);
+        const double rv = Arith<ARITH>::residual(sm.F[e], ue, sm.U[bu + kk], sm.U[o - 1], sm.U[bd + kk], uo, c, p.st);
         if (p.post == POST_INJECT) {
             const long kg = (long)tl.k0 + kk;
             p.crhs[(long)(q >> 1) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;         // gs.cpp:283
@@ -359,8 +349,8 @@ SP_FN void post_row(const Params& p, const Tile& tl, const Smem& sm, ThreadState
     }
     if (p.post == POST_NORM2 && (st.ok & 2u)) {          // odd column 2kg+1
         const Coef4 c = Arith<ARITH>::coef(sm.V1[o], sm.V2[o], p.st);
-        const double rv = Arith<ARITH>::residual(sm.F[o], uo, sm.U[rowix(su, 1) + kk], ue,
-                                                 sm.U[rowix(sd, 1) + kk], sm.U[e + 1], c, p.st);
+        const double rv = Arith<ARITH>::residual(sm.F[o], uo, sm.U[bu + p.SWK + kk], ue, sm.U[bd + p.SWK + kk],
+                                                 sm.U[e + 1], c, p.st);
         st.acc += rv * rv;
     }
 }
@@ -368,14 +358,16 @@ SP_FN void post_row(const Params& p, const Tile& tl, const Smem& sm, ThreadState
 // ------------------------------------------------------------------------------------------
 SP_FN int first_step(const Tile& tl) { return tl.R0; }
 SP_FN int last_step(const Params& p, const Tile& tl) { return tl.rb1 + 4 * p.K + 2; }
+SP_FN int num_groups(const Tile& tl) { return (tl.R1 - tl.R0) / GROUP + 1; }
 
-// producer prologue: the first DEPTH rows
+// producer prologue: the first two groups
 SP_FN void producer_prologue(const Params& p, const Tile& tl, const Smem& sm)
 {
-    for (int r = tl.R0; r < tl.R0 + DEPTH && r <= tl.R1; ++r) issue_row_loads(p, tl, sm, r);
+    const int ng = num_groups(tl);
+    for (int g = 0; g < 2 && g < ng; ++g) issue_group_loads(p, tl, sm, g);
 }
 
-// wait until row R0 has landed (every thread, before the first step)
+// wait until the first group has landed (every thread, before the first step)
 SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
 
 // everything a thread does in step t; a block barrier separates consecutive steps.  On entry row
@@ -387,10 +379,12 @@ SP_FN void thread_step(const Params& p, const Tile& tl, const Smem& sm, ThreadSt
         if (lane == 0) {
             const int q = t - 4 * p.K - 1;              // finished by the previous step
             if (p.write_u && q >= tl.rb0 && q <= tl.rb1) issue_row_store(p, tl, sm, q);
-            const int r = t + DEPTH;
-            if (r <= tl.R1) {
-                sp_store_wait_read2();                  // the slot's previous row has left shared memory
-                issue_row_loads(p, tl, sm, r);
+            // group g is requested LEAD steps before its first row: its ring slots were last read
+            // (row t-4K-3 and older) in the previous step
+            const int d = t + LEAD - tl.R0;
+            if (d % GROUP == 0 && d / GROUP >= 2 && d / GROUP < num_groups(tl)) {
+                sp_store_wait_read2();                  // the slots' previous rows have left shared memory
+                issue_group_loads(p, tl, sm, d / GROUP);
             }
         }
     } else if (st.role == ROLE_STAGE) {
@@ -404,17 +398,22 @@ SP_FN void thread_step(const Params& p, const Tile& tl, const Smem& sm, ThreadSt
         post_row<ARITH>(p, tl, sm, st);
     }
     st.row += 1;
-    st.slot = wrap_slot(st.slot + 1);
-    // row t+1 must have landed before anyone touches it in step t+1
-    st.wslot += 1;
-    if (st.wslot == RING) { st.wslot = 0; st.wpar ^= 1u; }
-    if (t + 1 <= tl.R1) sp_bar_wait(&sm.full[st.wslot], st.wpar);
+    st.base = ring_next(p, st.base);
+    // row t+1 must have landed before anyone touches it in step t+1: wait when it opens a new group
+    st.wphase += 1;
+    if (st.wphase == GROUP) {
+        st.wphase = 0;
+        st.wgroup += 1;
+        if (st.wgroup == NGROUP) { st.wgroup = 0; st.wpar ^= 1u; }
+        if (t + 1 <= tl.R1) sp_bar_wait(&sm.full[st.wgroup], st.wpar);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // Tile planner.  Cost model (relative): a tile takes (rows + fill) steps, a step costs
 // c0 + SWK (barrier latency + work proportional to the strip width); tiles run one per SM in
-// waves of `sms`.  Search strip width and band count for the cheapest plan.
+// waves of `sms`.  Search strip width (SWK a multiple of 16: TMA boxes land 128-byte aligned) and
+// band count for the cheapest plan.
 struct Plan { int WK, SWK, nstrips, nbands; long RBAND; };
 
 inline Plan make_plan(long n, int K, int sms)
@@ -422,7 +421,8 @@ inline Plan make_plan(long n, int K, int sms)
     const long npairs = n / 2 + 1, nrows = n + 1;
     Plan best{};
     double best_cost = 1e300;
-    for (int WK = 16; WK <= SWK_MAX - 2 * HK; WK += 4) {
+    for (int SWK = 32; SWK <= SWK_MAX; SWK += 16) {
+        const int WK = SWK - 2 * HK;
         const int nstrips = (int)((npairs + WK - 1) / WK);
         for (int nb = 1; nb <= 4096; nb = nb < 16 ? nb + 1 : nb * 2) {
             const long RB = (nrows + nb - 1) / nb;
@@ -430,9 +430,9 @@ inline Plan make_plan(long n, int K, int sms)
             const int nbands = (int)((nrows + RB - 1) / RB);
             const long tiles = (long)nstrips * nbands;
             const long waves = (tiles + sms - 1) / sms;
-            const double steps = (double)RB + 2.0 * (2 * K + 1) + 4.0 * K + 2.0 + DEPTH;
-            const double cost = (double)waves * steps * (40.0 + WK + 2 * HK);
-            if (cost < best_cost) { best_cost = cost; best = Plan{WK, WK + 2 * HK, nstrips, nbands, RB}; }
+            const double steps = (double)RB + 2.0 * (2 * K + 1) + 4.0 * K + 2.0 + 2 * GROUP;
+            const double cost = (double)waves * steps * (48.0 + SWK);
+            if (cost < best_cost) { best_cost = cost; best = Plan{WK, SWK, nstrips, nbands, RB}; }
         }
     }
     return best;

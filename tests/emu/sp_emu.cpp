@@ -32,7 +32,23 @@ int fail(int code, const std::string&) { return code; }
 long& launch_counter() { static long c = 0; return c; }
 namespace sp {
 SP_FN void sp_bar_expect(unsigned long long*, unsigned) {}
-SP_FN void sp_bulk_load(double* sdst, const double* gsrc, unsigned bytes, unsigned long long*) { std::memcpy(sdst, gsrc, bytes); }
+// software model of the 3-D tensor copy: box {inner, 2, rows} at (x, 0, z), zeros outside the tensor
+SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long*)
+{
+    const double* src = which == FIELD_U ? p.u_in : which == FIELD_F ? p.rhs : which == FIELD_V1 ? p.v1 : which == FIELD_V2 ? p.v2 : p.cu;
+    const bool coarse = which == FIELD_C;
+    const long odd = coarse ? p.codd : p.odd, pitch = coarse ? p.cpitch : p.pitch;
+    const long nrows = coarse ? p.nhalf + 1 : p.n + 1;
+    const int inner = coarse ? p.CW : p.SWK, brows = coarse ? CROWS : GROUP;
+    for (int zz = 0; zz < brows; ++zz)
+        for (int par = 0; par < 2; ++par)
+            for (int xx = 0; xx < inner; ++xx) {
+                const long gx = (long)x + xx, gz = (long)z + zz;
+                const bool in = gx >= 0 && gx < odd && gz >= 0 && gz < nrows;
+                sdst[((long)zz * 2 + par) * inner + xx] = in ? src[gz * pitch + par * odd + gx] : 0.0;
+            }
+}
+SP_FN void sp_tma_prefetch(const Params&, int, int, int) {}
 SP_FN void sp_bar_wait(unsigned long long*, unsigned) {}
 SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes) { std::memcpy(gdst, ssrc, bytes); }
 SP_FN void sp_store_commit() {}
@@ -64,7 +80,7 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
     if (nbands > 0) {
         pl.RBAND = (n + 1 + nbands - 1) / nbands; pl.nbands = (int)((n + 1 + pl.RBAND - 1) / pl.RBAND);
     }
-    if (pl.SWK > SWK_MAX || (pl.WK & 3)) return -1;
+    if (pl.SWK > SWK_MAX || (pl.SWK & 15)) return -1;
     p.RBAND = pl.RBAND; p.WK = pl.WK; p.SWK = pl.SWK; p.nstrips = pl.nstrips; p.nbands = pl.nbands;
     p.K = K; p.pre = cu ? 1 : 0; p.post = post; p.write_u = (K > 0 || cu) ? 1 : 0; p.u_is_zero = u_in ? 0 : 1;
     // Stencil exactly as make_stencil (solver.cu)
@@ -75,8 +91,8 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
         p.st.r = r; p.st.nu = nu; p.st.h = dx; p.st.diag = 1.0 - four_r_nu; p.st.diag_rhs = 1.0 + four_r_nu;
         p.st.inv_diag = 1.0 / p.st.diag; p.st.hr = r * dx * 0.5; p.st.rnu = r * nu;
     }
-    std::vector<double> zero(4 * SWK_MAX, 0.0);
-    p.u_in = u_in; p.rhs = rhs; p.v1 = v1; p.v2 = v2; p.cu = cu; p.zero_row = zero.data();
+    p.CW = pl.SWK / 2 + 8;
+    p.u_in = u_in; p.rhs = rhs; p.v1 = v1; p.v2 = v2; p.cu = cu;
     p.u_out = u_out; p.crhs = crhs; p.partials = partials;
     const long ntiles = (long)pl.nstrips * pl.nbands;
     std::vector<unsigned char> smem(SMEM_BYTES);

@@ -75,7 +75,7 @@ def fields(n, seed):
     return [rng.standard_normal((n + 1, n + 1)) for _ in range(4)]
 
 
-GEOMS = [(0, 0), (16, 1), (16, 3), (28, 2), (120, 5)]
+GEOMS = [(0, 0), (24, 1), (24, 3), (40, 2), (120, 5)]      # (owned pairs per strip = SWK - 8, bands)
 
 
 @pytest.mark.parametrize("n", [32, 64, 200, 256])
@@ -117,7 +117,7 @@ def test_zero_input_and_fast_arithmetic(emu, oracle):
     want = oracle.gauss_seidel(np.zeros((n + 1, n + 1)), rhs, n, v1, v2, dt, nu, dx, 3)
     got, _, _ = run(emu, n, None, rhs, v1, v2, 3, 1, 1, dt, nu, dx)          # u_in == NULL: u is zero
     assert np.array_equal(got, want)
-    gotf, _, _ = run(emu, n, None, rhs, v1, v2, 3, 1, 0, dt, nu, dx, wk=28, nbands=3, order=2)
+    gotf, _, _ = run(emu, n, None, rhs, v1, v2, 3, 1, 0, dt, nu, dx, wk=40, nbands=3, order=2)
     assert np.linalg.norm(gotf - want) <= 1e-13 * np.linalg.norm(want)
 
 
@@ -127,6 +127,6 @@ def test_residual_only_pass(emu, oracle):
     u, rhs, v1, v2 = fields(n, 9)
     dx = 1.0 / n; dt = dx / 10; nu = -4e-4
     want = oracle.norm(oracle.residual(u, rhs, n, v1, v2, dt, nu, dx), n) ** 2
-    got_u, _, parts = run(emu, n, u, rhs, v1, v2, 0, 2, 1, dt, nu, dx, wk=20, nbands=2)
+    got_u, _, parts = run(emu, n, u, rhs, v1, v2, 0, 2, 1, dt, nu, dx, wk=24, nbands=2)
     assert np.isnan(got_u).all()
     assert abs(parts.sum() - want) <= 1e-12 * want
