@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -60,12 +61,12 @@ SP_FN void sp_store_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2
 SP_FN void sp_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int ARITH>
-__global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double scratch[32];
     Smem sm;
-    carve(sm, smem_raw);
+    carve(sm, smem_raw, p.SWK);
     const Tile tl = make_tile(p, blockIdx.x);
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     if (tid == PRODUCER_WARP * 32) producer_prologue(p, tl, sm);
     ThreadState st = init_thread(p, tl, tid);
     wait_first_row(sm);
+    first_prefetch(p, tl, sm, st);
     const int t1 = last_step(p, tl);
     for (int t = first_step(tl); t <= t1; ++t) {
         thread_step<ARITH>(p, tl, sm, st, t, lane);
@@ -122,7 +124,11 @@ static const Plan& plan_for(long n, int K)
     std::lock_guard<std::mutex> lock(mu);
     auto key = std::make_pair(n, K);
     auto it = cache.find(key);
-    if (it == cache.end()) it = cache.emplace(key, make_plan(n, K, g_sms > 0 ? g_sms : 148)).first;
+    if (it == cache.end()) {
+        int force = 0;
+        if (const char* e = getenv("MGB200_SWK")) force = atoi(e);       // tuning aid: pin the strip width
+        it = cache.emplace(key, make_plan(n, K, g_sms > 0 ? g_sms : 148, force)).first;
+    }
     return it->second;
 }
 
@@ -192,8 +198,9 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
     if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "stream_pass: POST_INJECT without coarse_rhs");
     if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "stream_pass: POST_NORM2 without partials");
     const unsigned grid = (unsigned)(pl.nstrips * pl.nbands);
-    if (a.arith == MGB200_ARITH_EXACT) k_stream_pass<MGB200_ARITH_EXACT><<<grid, THREADS, SMEM_BYTES, s>>>(p);
-    else k_stream_pass<MGB200_ARITH_FAST><<<grid, THREADS, SMEM_BYTES, s>>>(p);
+    const size_t smem = smem_bytes(pl.SWK);
+    if (a.arith == MGB200_ARITH_EXACT) k_stream_pass<MGB200_ARITH_EXACT><<<grid, THREADS, smem, s>>>(p);
+    else k_stream_pass<MGB200_ARITH_FAST><<<grid, THREADS, smem, s>>>(p);
     return check_launch("k_stream_pass");
 }
 

@@ -99,20 +99,25 @@ struct Smem {
 
 enum Field { FIELD_U = 0, FIELD_F = 1, FIELD_V1 = 2, FIELD_V2 = 3, FIELD_C = 4 };
 
-constexpr size_t SMEM_BYTES = (size_t)4 * RING * 2 * SWK_MAX * 8 + (size_t)NGROUP * CROWS * 2 * CW_MAX * 8 + NGROUP * 8 + 128;
+// dynamic shared memory of a tile with SWK pairs per row (all sub-arrays 128-byte aligned)
+constexpr size_t smem_bytes(int swk)
+{
+    return (size_t)4 * RING * 2 * swk * 8 + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8) * 8 + NGROUP * 8 + 128;
+}
+constexpr size_t SMEM_BYTES = smem_bytes(SWK_MAX);
 
 struct alignas(16) D2 { double x, y; };    // 16-byte vector; aligned accesses only (even pair index)
 
 SP_FN D2 ld2(const double* p) { return *reinterpret_cast<const D2*>(p); }
 SP_FN void st2(double* p, D2 v) { *reinterpret_cast<D2*>(p) = v; }
 
-SP_FN void carve(Smem& sm, unsigned char* base)
+SP_FN void carve(Smem& sm, unsigned char* base, int swk)
 {
-    const size_t row = (size_t)RING * 2 * SWK_MAX;
+    const size_t row = (size_t)RING * 2 * swk;
     double* d = reinterpret_cast<double*>(base);
     sm.U = d; sm.F = d + row; sm.V1 = d + 2 * row; sm.V2 = d + 3 * row;
     sm.C = d + 4 * row;
-    sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)NGROUP * CROWS * 2 * CW_MAX);
+    sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8));
 }
 
 SP_FN Tile make_tile(const Params& p, long tile)
@@ -208,6 +213,7 @@ struct ThreadState {
     int wgroup;    // its group slot
     unsigned wpar; // and that barrier's phase parity
     double acc;    // POST_NORM2 accumulator
+    D2 pf[2][3];   // stage warps: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -256,6 +262,25 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, int tid)
 SP_FN int ring_next(const Params& p, int base) { const int b = base + 2 * p.SWK; return b == RING * 2 * p.SWK ? 0 : b; }
 SP_FN int ring_prev(const Params& p, int base) { return (base == 0 ? RING * 2 * p.SWK : base) - 2 * p.SWK; }
 
+// Stage warps fetch rhs, v1, v2 of their NEXT row's targets before the step barrier: those fields
+// never change, the row landed long ago (row t-1-2s at step t), and the loads then overlap the
+// barrier wait instead of sitting on the critical path of the next step.
+SP_FN void stage_prefetch(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st)
+{
+    const int i = st.row;                                             // already advanced to the next row
+    if (st.idx >= 2 * p.K || i <= tl.R0 || i >= tl.R1) return;
+    const int par = (st.idx + i) & 1;
+    const int bc = st.base + (par ? p.SWK : 0);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int kk = st.kk + 64 * g;
+        if (kk >= p.SWK) continue;
+        st.pf[g][0] = ld2(sm.F + bc + kk);
+        st.pf[g][1] = ld2(sm.V1 + bc + kk);
+        st.pf[g][2] = ld2(sm.V2 + bc + kk);
+    }
+}
+
 // one half-sweep stage on row st.row: colour = stage & 1; two 16-byte vectors per lane
 template <int ARITH>
 SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const ThreadState& st)
@@ -267,22 +292,20 @@ SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const Thre
     const int pofs = par ? p.SWK : 0;
     const int bc = st.base + pofs, bo = st.base + (p.SWK - pofs);     // this parity / the other parity of row i
     const int bu = ring_prev(p, st.base) + pofs, bd = ring_next(p, st.base) + pofs;
+    // even columns: left = O[kk-1], right = O[kk]; odd columns: left = E[kk], right = E[kk+1]:
+    // with mid = other[kk..kk+1] the missing neighbour is other[kk-1] (even) or other[kk+2] (odd)
+    const int xo = par ? 2 : -1;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-        const unsigned okg = (ok >> (2 * g)) & 3u;
-        if (okg == 0) continue;
         const int kk = st.kk + 64 * g;
-        const D2 up = ld2(sm.U + bu + kk), dn = ld2(sm.U + bd + kk);
-        const D2 f = ld2(sm.F + bc + kk), w1 = ld2(sm.V1 + bc + kk), w2 = ld2(sm.V2 + bc + kk);
-        const D2 mid = ld2(sm.U + bo + kk);                           // other parity, same pair indices
-        double lf0, rt0, lf1, rt1;
-        if (par == 0) {            // even columns: left = O[kk-1], right = O[kk]
-            const double prev = (okg & 1u) ? sm.U[bo + kk - 1] : 0.0;
-            lf0 = prev; rt0 = mid.x; lf1 = mid.x; rt1 = mid.y;
-        } else {                   // odd columns: left = E[kk], right = E[kk+1]
-            const double next = (okg & 2u) ? sm.U[bo + kk + 2] : 0.0;
-            lf0 = mid.x; rt0 = mid.y; lf1 = mid.y; rt1 = next;
-        }
+        if (kk >= p.SWK) continue;                                    // warp-uniform only when SWK <= 64
+        const unsigned okg = (ok >> (2 * g)) & 3u;
+        const D2 up = ld2(sm.U + bu + kk), dn = ld2(sm.U + bd + kk), mid = ld2(sm.U + bo + kk);
+        const int xi = kk + xo;
+        const double ext = sm.U[bo + (xi < 0 ? 0 : xi)];              // clamped: an unused lane may read any staged cell
+        const D2 f = st.pf[g][0], w1 = st.pf[g][1], w2 = st.pf[g][2];
+        const double lf0 = par ? mid.x : ext, rt0 = par ? mid.y : mid.x;
+        const double lf1 = par ? mid.y : mid.x, rt1 = par ? ext : mid.y;
         const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
         const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
         D2 out;
@@ -290,7 +313,7 @@ SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const Thre
         out.y = Arith<ARITH>::gs(f.y, up.y, lf1, dn.y, rt1, c1, p.st);
         if (okg == 3u) st2(sm.U + bc + kk, out);
         else if (okg == 1u) sm.U[bc + kk] = out.x;
-        else sm.U[bc + kk + 1] = out.y;
+        else if (okg == 2u) sm.U[bc + kk + 1] = out.y;
     }
 }
 
@@ -369,6 +392,11 @@ SP_FN void producer_prologue(const Params& p, const Tile& tl, const Smem& sm)
 
 // wait until the first group has landed (every thread, before the first step)
 SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
+// after wait_first_row: the stage warps' operand fetch for the very first step
+SP_FN void first_prefetch(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st)
+{
+    if (st.role == ROLE_STAGE) stage_prefetch(p, tl, sm, st);
+}
 
 // everything a thread does in step t; a block barrier separates consecutive steps.  On entry row
 // t has landed (awaited at the end of the previous step).
@@ -399,6 +427,7 @@ SP_FN void thread_step(const Params& p, const Tile& tl, const Smem& sm, ThreadSt
     }
     st.row += 1;
     st.base = ring_next(p, st.base);
+    if (st.role == ROLE_STAGE) stage_prefetch(p, tl, sm, st);
     // row t+1 must have landed before anyone touches it in step t+1: wait when it opens a new group
     st.wphase += 1;
     if (st.wphase == GROUP) {
@@ -416,22 +445,30 @@ SP_FN void thread_step(const Params& p, const Tile& tl, const Smem& sm, ThreadSt
 // band count for the cheapest plan.
 struct Plan { int WK, SWK, nstrips, nbands; long RBAND; };
 
-inline Plan make_plan(long n, int K, int sms)
+// resident tiles per SM for a strip width (shared memory is the limit; 227 KB per SM)
+inline int tiles_per_sm(int swk) { const int k = (int)(232448 / (smem_bytes(swk) + 1024)); return k < 1 ? 1 : (k > 2 ? 2 : k); }
+
+inline Plan make_plan(long n, int K, int sms, int force_swk = 0)
 {
     const long npairs = n / 2 + 1, nrows = n + 1;
     Plan best{};
     double best_cost = 1e300;
     for (int SWK = 32; SWK <= SWK_MAX; SWK += 16) {
+        if (force_swk && SWK != force_swk) continue;
         const int WK = SWK - 2 * HK;
+        const int slots = sms * tiles_per_sm(SWK);
         const int nstrips = (int)((npairs + WK - 1) / WK);
         for (int nb = 1; nb <= 4096; nb = nb < 16 ? nb + 1 : nb * 2) {
             const long RB = (nrows + nb - 1) / nb;
             if (nb > 1 && RB < 32) break;
             const int nbands = (int)((nrows + RB - 1) / RB);
             const long tiles = (long)nstrips * nbands;
-            const long waves = (tiles + sms - 1) / sms;
+            const long waves = (tiles + slots - 1) / slots;
             const double steps = (double)RB + 2.0 * (2 * K + 1) + 4.0 * K + 2.0 + 2 * GROUP;
-            const double cost = (double)waves * steps * (48.0 + SWK);
+            // a step costs a fixed latency plus work proportional to the strip width; two
+            // co-resident tiles hide each other's latency but share the SM's throughput
+            const double per_step = tiles_per_sm(SWK) == 2 ? 48.0 + 2.0 * SWK : 96.0 + SWK;
+            const double cost = (double)waves * steps * per_step;
             if (cost < best_cost) { best_cost = cost; best = Plan{WK, SWK, nstrips, nbands, RB}; }
         }
     }

@@ -102,12 +102,13 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
         double* sd = reinterpret_cast<double*>(smem.data());
         for (size_t q = 0; q < SMEM_BYTES / 8; ++q) sd[q] = std::numeric_limits<double>::quiet_NaN();
         Smem sm;
-        carve(sm, smem.data());
+        carve(sm, smem.data(), p.SWK);
         const Tile tl = make_tile(p, tile);
         producer_prologue(p, tl, sm);
         std::vector<ThreadState> st(THREADS);
         for (int tid = 0; tid < THREADS; ++tid) st[tid] = init_thread(p, tl, tid);
         wait_first_row(sm);
+        for (int tid = 0; tid < THREADS; ++tid) first_prefetch(p, tl, sm, st[tid]);
         const int t1 = last_step(p, tl);
         for (int t = first_step(tl); t <= t1; ++t) {
             std::iota(perm.begin(), perm.end(), 0);
