@@ -60,6 +60,38 @@ SP_FN void sp_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "m
 SP_FN void sp_store_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 SP_FN void sp_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+SP_FN D2 sp_lds2(const Smem& sm, unsigned off)
+{
+    D2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sm.base32 + off));
+    return v;
+}
+SP_FN double sp_lds1(const Smem& sm, unsigned off)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm.base32 + off));
+    return v;
+}
+SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(sm.base32 + off), "d"(v.x), "d"(v.y) : "memory");
+}
+SP_FN void sp_sts1(const Smem& sm, unsigned off, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm.base32 + off), "d"(v) : "memory");
+}
+
+template <int ARITH, int NG>
+__device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int lane)
+{
+    const int t1 = last_step(p, tl);
+    for (int t = first_step(tl); t <= t1; ++t) {
+        role_step<ARITH, NG>(p, tl, geo, sm, st, t, lane);
+        end_step(tl, geo, sm, st, t);
+        __syncthreads();
+    }
+}
+
 template <int ARITH>
 __global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constant__ Params p)
 {
@@ -67,7 +99,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constan
     __shared__ double scratch[32];
     Smem sm;
     carve(sm, smem_raw, p.SWK);
+    sm.base32 = smem_u32(smem_raw);
     const Tile tl = make_tile(p, blockIdx.x);
+    const Geo geo = make_geo(p);
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < NGROUP; ++s)
@@ -77,14 +111,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constan
     }
     __syncthreads();
     if (tid == PRODUCER_WARP * 32) producer_prologue(p, tl, sm);
-    ThreadState st = init_thread(p, tl, tid);
+    ThreadState st = init_thread(p, tl, geo, tid);
     wait_first_row(sm);
-    first_prefetch(p, tl, sm, st);
-    const int t1 = last_step(p, tl);
-    for (int t = first_step(tl); t <= t1; ++t) {
-        thread_step<ARITH>(p, tl, sm, st, t, lane);
-        __syncthreads();
-    }
+    if (p.SWK > 64) run_tile<ARITH, 2>(p, tl, geo, sm, st, lane);
+    else run_tile<ARITH, 1>(p, tl, geo, sm, st, lane);
     if (tid == PRODUCER_WARP * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.post == POST_NORM2) {
         const double tot = block_sum(st.acc, scratch);

@@ -89,6 +89,8 @@ struct Tile {
 };
 
 struct Smem {
+    unsigned char* raw;        // start of the dynamic shared memory (the U ring)
+    unsigned base32;           // its shared-space address (device only)
     double* U;                 // [RING][2][SWK]
     double* F;                 // rhs
     double* V1;
@@ -108,13 +110,12 @@ constexpr size_t SMEM_BYTES = smem_bytes(SWK_MAX);
 
 struct alignas(16) D2 { double x, y; };    // 16-byte vector; aligned accesses only (even pair index)
 
-SP_FN D2 ld2(const double* p) { return *reinterpret_cast<const D2*>(p); }
-SP_FN void st2(double* p, D2 v) { *reinterpret_cast<D2*>(p) = v; }
 
 SP_FN void carve(Smem& sm, unsigned char* base, int swk)
 {
     const size_t row = (size_t)RING * 2 * swk;
     double* d = reinterpret_cast<double*>(base);
+    sm.raw = base; sm.base32 = 0;
     sm.U = d; sm.F = d + row; sm.V1 = d + 2 * row; sm.V2 = d + 3 * row;
     sm.C = d + 4 * row;
     sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8));
@@ -136,7 +137,6 @@ SP_FN Tile make_tile(const Params& p, long tile)
     return tl;
 }
 
-SP_FN int wrap_slot(int s) { return s >= RING ? s - RING : (s < 0 ? s + RING : s); }
 SP_FN int ring_slot(const Tile& tl, int row) { return (row - tl.R0) % RING; }
 
 
@@ -153,6 +153,12 @@ SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes);
 SP_FN void sp_store_commit();
 SP_FN void sp_store_wait_read2();
 SP_FN void sp_fence_async();
+// shared-memory accesses by byte offset from the start of the U ring (16-byte vectors need
+// 16-byte aligned offsets); on the device these are ld/st.shared with register+immediate addresses
+SP_FN D2 sp_lds2(const Smem& sm, unsigned off);
+SP_FN double sp_lds1(const Smem& sm, unsigned off);
+SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v);
+SP_FN void sp_sts1(const Smem& sm, unsigned off, double v);
 
 // ------------------------------------------------------------------------------------------
 // producer: request group g (rows R0+4g .. R0+4g+3) of the four fields, plus the three coarse rows
@@ -199,21 +205,38 @@ SP_FN void issue_row_store(const Params& p, const Tile& tl, const Smem& sm, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// per-thread state, advanced by one row per step
+// per-thread state, advanced by one row per step.  Rows are addressed by BYTE OFFSETS into the U
+// ring that walk the ring incrementally; the rhs / v1 / v2 rings sit at +ringb, +2 ringb, +3 ringb.
 enum Role { ROLE_STAGE = 0, ROLE_PRE = 1, ROLE_POST = 2, ROLE_PRODUCER = 3 };
+
+struct Geo {
+    unsigned swkb;    // bytes of one parity run: SWK * 8
+    unsigned rowb;    // bytes of one ring row (both runs)
+    unsigned ringb;   // bytes of one field's ring
+};
+SP_FN Geo make_geo(const Params& p)
+{
+    Geo g;
+    g.swkb = (unsigned)p.SWK * 8u; g.rowb = 2u * g.swkb; g.ringb = (unsigned)RING * g.rowb;
+    return g;
+}
 
 struct ThreadState {
     int role;
-    int idx;       // stage number / chunk number
-    int kk;        // first local pair handled (stage: also kk + 64)
-    int row;       // the role's row at the current step
-    int base;      // element offset of that row's even run in the ring: slot * 2 * SWK
-    unsigned ok;   // validity bits (role specific)
-    int wphase;    // (row awaited at the end of the step - R0) mod GROUP
-    int wgroup;    // its group slot
-    unsigned wpar; // and that barrier's phase parity
-    double acc;    // POST_NORM2 accumulator
-    D2 pf[2][3];   // stage warps: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
+    int idx;            // stage number / chunk number
+    int kk;             // first local pair handled (stage: also kk + 64)
+    int row;            // the role's row at the current step
+    int lo, hi;         // rows on which the role acts: [lo, hi]
+    unsigned a_prev, a_cur, a_next;   // offsets of even-run element kk of rows row-1, row, row+1
+    unsigned lim;       // ringb + kk*8: wrap limit of those offsets
+    unsigned ok_cur;    // validity bits for this step's column parity (stage) / role specific
+    unsigned ok_nxt;    // stage: validity bits for the next step's parity
+    int par;            // stage: column parity of the colour in `row`
+    int wphase;         // (row awaited at the end of the step - R0) mod GROUP
+    int wgroup;         // its group slot
+    unsigned wpar;      // and that barrier's phase parity
+    double acc;         // POST_NORM2 accumulator
+    D2 pf[2][3];        // stage: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -225,155 +248,169 @@ SP_FN bool target_ok(const Params& p, const Tile& tl, int kk, int par)
     return kk <= p.SWK - 2 && kg >= 0 && kg <= p.nhalf - 1;                 // odd column 2kg+1: neighbours E[kk], E[kk+1]
 }
 
-SP_FN ThreadState init_thread(const Params& p, const Tile& tl, int tid)
+SP_FN unsigned ring_adv(unsigned a, const Geo& g, unsigned lim)
+{
+    a += g.rowb;
+    return a >= lim ? a - g.ringb : a;
+}
+
+SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, int tid)
 {
     ThreadState s;
     const int warp = tid >> 5, lane = tid & 31;
-    s.acc = 0.0; s.ok = 0; s.idx = 0; s.kk = 0;
-    int off;                                             // role row = t - off
+    s.acc = 0.0; s.ok_cur = 0; s.ok_nxt = 0; s.idx = 0; s.kk = 0; s.par = 0;
+    s.lo = 1; s.hi = 0;                                  // empty range
+    int off = 0;                                         // role row = t - off
     if (warp < NSTAGE) {
         s.role = ROLE_STAGE; s.idx = warp; s.kk = 2 * lane; off = 2 + 2 * warp;
-        for (int g = 0; g < 2; ++g)
-            for (int e = 0; e < 2; ++e)
-                for (int par = 0; par < 2; ++par)
-                    if (target_ok(p, tl, s.kk + 64 * g + e, par)) s.ok |= 1u << (par * 4 + g * 2 + e);
+        if (warp < 2 * p.K) { s.lo = tl.R0 + 1; s.hi = tl.R1 - 1; }        // rows row-1, row+1 must be staged
     } else if (warp < NSTAGE + NPRE) {
         s.role = ROLE_PRE; s.idx = warp - NSTAGE; s.kk = 64 * s.idx + 2 * lane; off = 0;
         for (int e = 0; e < 2; ++e) {
             const long kg = (long)tl.k0 + s.kk + e;
-            if (s.kk + e < p.SWK && kg >= 0 && kg <= p.nhalf - 1) s.ok |= 1u << e;          // pair holds an interior odd column
-            if (s.kk + e < p.SWK && kg >= 1 && kg <= p.nhalf - 1) s.ok |= 1u << (2 + e);    // ... and an interior even column
+            if (s.kk + e < p.SWK && kg >= 0 && kg <= p.nhalf - 1) s.ok_cur |= 1u << e;          // pair holds an interior odd column
+            if (s.kk + e < p.SWK && kg >= 1 && kg <= p.nhalf - 1) s.ok_cur |= 1u << (2 + e);    // ... and an interior even column
         }
+        if (p.pre && (s.ok_cur & 3u)) { s.lo = tl.R0 < 1 ? 1 : tl.R0; s.hi = tl.R1 > p.n - 1 ? (int)p.n - 1 : tl.R1; }
     } else if (warp < NSTAGE + NPRE + NPOST) {
         s.role = ROLE_POST; s.idx = warp - NSTAGE - NPRE; s.kk = HK + 32 * s.idx + lane; off = 4 * p.K + 2;
         if (s.kk < HK + p.WK) {                          // owned pairs only
-            if (target_ok(p, tl, s.kk, 0)) s.ok |= 1u;
-            if (target_ok(p, tl, s.kk, 1)) s.ok |= 2u;
+            if (target_ok(p, tl, s.kk, 0)) s.ok_cur |= 1u;
+            if (p.post == POST_NORM2 && target_ok(p, tl, s.kk, 1)) s.ok_cur |= 2u;
         }
+        if (p.post != POST_NONE && s.ok_cur) { s.lo = tl.rb0 < 1 ? 1 : tl.rb0; s.hi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1; }
     } else {
-        s.role = ROLE_PRODUCER; off = 0;
+        s.role = ROLE_PRODUCER;
     }
     s.row = tl.R0 - off;
-    s.base = (((RING - off) % RING + RING) % RING) * 2 * p.SWK;      // row R0 sits in slot 0
+    const int slot = ((RING - off) % RING + RING) % RING;               // row R0 sits in slot 0
+    s.lim = geo.ringb + (unsigned)s.kk * 8u;
+    s.a_cur = (unsigned)slot * geo.rowb + (unsigned)s.kk * 8u;
+    s.a_next = ring_adv(s.a_cur, geo, s.lim);
+    s.a_prev = (slot == 0 ? (unsigned)(RING - 1) : (unsigned)(slot - 1)) * geo.rowb + (unsigned)s.kk * 8u;
+    if (s.role == ROLE_STAGE) {
+        s.par = (s.idx + s.row) & 1;
+        for (int g = 0; g < 2; ++g)
+            for (int e = 0; e < 2; ++e) {
+                if (target_ok(p, tl, s.kk + 64 * g + e, s.par)) s.ok_cur |= 1u << (g * 2 + e);
+                if (target_ok(p, tl, s.kk + 64 * g + e, s.par ^ 1)) s.ok_nxt |= 1u << (g * 2 + e);
+            }
+    }
     s.wphase = 0; s.wgroup = 0; s.wpar = 0;
     return s;
 }
 
-SP_FN int ring_next(const Params& p, int base) { const int b = base + 2 * p.SWK; return b == RING * 2 * p.SWK ? 0 : b; }
-SP_FN int ring_prev(const Params& p, int base) { return (base == 0 ? RING * 2 * p.SWK : base) - 2 * p.SWK; }
-
+// ------------------------------------------------------------------------------------------
 // Stage warps fetch rhs, v1, v2 of their NEXT row's targets before the step barrier: those fields
 // never change, the row landed long ago (row t-1-2s at step t), and the loads then overlap the
-// barrier wait instead of sitting on the critical path of the next step.
-SP_FN void stage_prefetch(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st)
+// barrier wait instead of sitting on the critical path of the next step.  PARN = parity of the
+// colour in that next row.
+template <int NG, int PARN>
+SP_FN void stage_prefetch(const Geo& geo, const Smem& sm, ThreadState& st)
 {
-    const int i = st.row;                                             // already advanced to the next row
-    if (st.idx >= 2 * p.K || i <= tl.R0 || i >= tl.R1) return;
-    const int par = (st.idx + i) & 1;
-    const int bc = st.base + (par ? p.SWK : 0);
+    if (st.row + 1 < st.lo || st.row + 1 > st.hi) return;
+    const unsigned b = st.a_next + (PARN ? geo.swkb : 0u) + geo.ringb;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int kk = st.kk + 64 * g;
-        if (kk >= p.SWK) continue;
-        st.pf[g][0] = ld2(sm.F + bc + kk);
-        st.pf[g][1] = ld2(sm.V1 + bc + kk);
-        st.pf[g][2] = ld2(sm.V2 + bc + kk);
+    for (int g = 0; g < NG; ++g) {
+        st.pf[g][0] = sp_lds2(sm, b + 512u * g);
+        st.pf[g][1] = sp_lds2(sm, b + geo.ringb + 512u * g);
+        st.pf[g][2] = sp_lds2(sm, b + 2u * geo.ringb + 512u * g);
     }
 }
 
-// one half-sweep stage on row st.row: colour = stage & 1; two 16-byte vectors per lane
-template <int ARITH>
-SP_FN void stage_row(const Params& p, const Tile& tl, const Smem& sm, const ThreadState& st)
+// One half-sweep stage on row st.row (colour = stage & 1), NG 16-byte vectors per lane, PAR = the
+// column parity of the colour in this row.  With pair index kk even, the horizontal neighbours of
+// targets (kk, kk+1) are three consecutive nodes of the OTHER run: from kk-1 (even columns:
+// O[kk-1], O[kk], O[kk+1]) or from kk (odd columns: E[kk], E[kk+1], E[kk+2]).
+template <int ARITH, int NG, int PAR>
+SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
-    const int i = st.row;
-    if (st.idx >= 2 * p.K || i <= tl.R0 || i >= tl.R1) return;      // rows i-1 and i+1 must be staged
-    const int par = (st.idx + i) & 1;                                 // column parity of this colour in row i
-    const unsigned ok = (st.ok >> (par * 4)) & 15u;
-    const int pofs = par ? p.SWK : 0;
-    const int bc = st.base + pofs, bo = st.base + (p.SWK - pofs);     // this parity / the other parity of row i
-    const int bu = ring_prev(p, st.base) + pofs, bd = ring_next(p, st.base) + pofs;
-    // even columns: left = O[kk-1], right = O[kk]; odd columns: left = E[kk], right = E[kk+1]:
-    // with mid = other[kk..kk+1] the missing neighbour is other[kk-1] (even) or other[kk+2] (odd)
-    const int xo = par ? 2 : -1;
+    if (st.row >= st.lo && st.row <= st.hi) {
+        const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const int kk = st.kk + 64 * g;
-        if (kk >= p.SWK) continue;                                    // warp-uniform only when SWK <= 64
-        const unsigned okg = (ok >> (2 * g)) & 3u;
-        const D2 up = ld2(sm.U + bu + kk), dn = ld2(sm.U + bd + kk), mid = ld2(sm.U + bo + kk);
-        const int xi = kk + xo;
-        const double ext = sm.U[bo + (xi < 0 ? 0 : xi)];              // clamped: an unused lane may read any staged cell
-        const D2 f = st.pf[g][0], w1 = st.pf[g][1], w2 = st.pf[g][2];
-        const double lf0 = par ? mid.x : ext, rt0 = par ? mid.y : mid.x;
-        const double lf1 = par ? mid.y : mid.x, rt1 = par ? ext : mid.y;
-        const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
-        const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
-        D2 out;
-        out.x = Arith<ARITH>::gs(f.x, up.x, lf0, dn.x, rt0, c0, p.st);
-        out.y = Arith<ARITH>::gs(f.y, up.y, lf1, dn.y, rt1, c1, p.st);
-        if (okg == 3u) st2(sm.U + bc + kk, out);
-        else if (okg == 1u) sm.U[bc + kk] = out.x;
-        else if (okg == 2u) sm.U[bc + kk + 1] = out.y;
+        for (int g = 0; g < NG; ++g) {
+            const unsigned go = 512u * g;
+            const D2 up = sp_lds2(sm, st.a_prev + po + go), dn = sp_lds2(sm, st.a_next + po + go);
+            double n0, n1, n2;
+            if (PAR == 0) {
+                n0 = sp_lds1(sm, st.a_cur + oo + go - 8u);
+                const D2 m = sp_lds2(sm, st.a_cur + oo + go);
+                n1 = m.x; n2 = m.y;
+            } else {
+                const D2 m = sp_lds2(sm, st.a_cur + oo + go);
+                n0 = m.x; n1 = m.y;
+                n2 = sp_lds1(sm, st.a_cur + oo + go + 16u);
+            }
+            const D2 f = st.pf[g][0], w1 = st.pf[g][1], w2 = st.pf[g][2];
+            const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
+            const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
+            D2 out;
+            out.x = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
+            out.y = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
+            const unsigned okg = (st.ok_cur >> (2 * g)) & 3u;
+            if (okg == 3u) sp_sts2(sm, st.a_cur + po + go, out);
+            else if (okg == 1u) sp_sts1(sm, st.a_cur + po + go, out.x);
+            else if (okg == 2u) sp_sts1(sm, st.a_cur + po + go + 8u, out.y);
+        }
     }
+    stage_prefetch<NG, PAR ^ 1>(geo, sm, st);
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
 // The coarse rows of a group start at coarse row (first fine row of the group) >> 1; coarse column
 // (k0 + kk) sits at local index kk: even kk in the E run at kk/2, odd kk in the O run at kk/2.
-SP_FN void prolong_row(const Params& p, const Tile& tl, const Smem& sm, const ThreadState& st)
+SP_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const int t = st.row;
-    if (!p.pre || (st.ok & 3u) == 0 || t < 1 || t > p.n - 1 || t < tl.R0 || t > tl.R1) return;
-    const int kk = st.kk, a = kk >> 1;                  // kk even
+    if (t < st.lo || t > st.hi) return;
     const int g = (t - tl.R0) / GROUP;
-    const int crow = (t >> 1) - ((tl.R0 + GROUP * g) >> 1);           // 0..1; the row below it is crow+1
-    const int c0 = ((g % NGROUP) * CROWS + crow) * 2 * p.CW, c1 = c0 + 2 * p.CW;
-    const int be = st.base, bo = st.base + p.SWK;
+    const int crow = (t >> 1) - ((tl.R0 + GROUP * g) >> 1);            // 0..2; an odd fine row also uses crow+1
+    const unsigned cwb = (unsigned)p.CW * 8u;
+    const unsigned c0 = 4u * geo.ringb + (unsigned)((g % NGROUP) * CROWS + crow) * 2u * cwb + (unsigned)(st.kk >> 1) * 8u;
+    const unsigned c1 = c0 + 2u * cwb;
     // coarse columns kk, kk+1, kk+2 of coarse row I (and I+1 for an odd fine row)
-    const double a0 = sm.C[c0 + a], a1 = sm.C[c0 + p.CW + a], a2 = sm.C[c0 + a + 1];
-    D2 ue = ld2(sm.U + be + kk), uo = ld2(sm.U + bo + kk);
+    const double a0 = sp_lds1(sm, c0), a1 = sp_lds1(sm, c0 + cwb), a2 = sp_lds1(sm, c0 + 8u);
+    const D2 ue = sp_lds2(sm, st.a_cur), uo = sp_lds2(sm, st.a_cur + geo.swkb);
     double e0, e1, o0, o1;
     if ((t & 1) == 0) {
         e0 = a0; e1 = a1;                                                                   // gs.cpp:238
         o0 = __dmul_rn(__dadd_rn(a0, a1), 0.5); o1 = __dmul_rn(__dadd_rn(a1, a2), 0.5);     // gs.cpp:240
     } else {
-        const double b0 = sm.C[c1 + a], b1 = sm.C[c1 + p.CW + a], b2 = sm.C[c1 + a + 1];
+        const double b0 = sp_lds1(sm, c1), b1 = sp_lds1(sm, c1 + cwb), b2 = sp_lds1(sm, c1 + 8u);
         e0 = __dmul_rn(__dadd_rn(a0, b0), 0.5); e1 = __dmul_rn(__dadd_rn(a1, b1), 0.5);     // gs.cpp:239
         o0 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a0, b0), a1), b1), 0.25);              // gs.cpp:241
         o1 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a1, b1), a2), b2), 0.25);
     }
-    if (st.ok & 4u) sm.U[be + kk] = __dadd_rn(ue.x, e0);                                    // multigrid.cpp:83
-    if (st.ok & 8u) sm.U[be + kk + 1] = __dadd_rn(ue.y, e1);
-    if (st.ok & 1u) sm.U[bo + kk] = __dadd_rn(uo.x, o0);
-    if (st.ok & 2u) sm.U[bo + kk + 1] = __dadd_rn(uo.y, o1);
+    if (st.ok_cur & 4u) sp_sts1(sm, st.a_cur, __dadd_rn(ue.x, e0));                         // multigrid.cpp:83
+    if (st.ok_cur & 8u) sp_sts1(sm, st.a_cur + 8u, __dadd_rn(ue.y, e1));
+    if (st.ok_cur & 1u) sp_sts1(sm, st.a_cur + geo.swkb, __dadd_rn(uo.x, o0));
+    if (st.ok_cur & 2u) sp_sts1(sm, st.a_cur + geo.swkb + 8u, __dadd_rn(uo.y, o1));
 }
 
 // residual epilogue on finished row q: injection into the coarse rhs or sum of squares
 template <int ARITH>
-SP_FN void post_row(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st)
+SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const int q = st.row;
-    const int lo = tl.rb0 < 1 ? 1 : tl.rb0, hi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1;
-    if (p.post == POST_NONE || st.ok == 0 || q < lo || q > hi) return;
+    if (q < st.lo || q > st.hi) return;
     if (p.post == POST_INJECT && (q & 1)) return;
-    const int kk = st.kk;
-    const int bu = ring_prev(p, st.base), bd = ring_next(p, st.base);
-    const int e = st.base + kk, o = st.base + p.SWK + kk;
-    const double ue = sm.U[e], uo = sm.U[o];
-    if (st.ok & 1u) {                                    // even column 2kg
-        const Coef4 c = Arith<ARITH>::coef(sm.V1[e], sm.V2[e], p.st);
-        const double rv = Arith<ARITH>::residual(sm.F[e], ue, sm.U[bu + kk], sm.U[o - 1], sm.U[bd + kk], uo, c, p.st);
+    const unsigned e = st.a_cur, o = st.a_cur + geo.swkb;
+    const double ue = sp_lds1(sm, e), uo = sp_lds1(sm, o);
+    if (st.ok_cur & 1u) {                                // even column 2kg
+        const Coef4 c = Arith<ARITH>::coef(sp_lds1(sm, e + 2u * geo.ringb), sp_lds1(sm, e + 3u * geo.ringb), p.st);
+        const double rv = Arith<ARITH>::residual(sp_lds1(sm, e + geo.ringb), ue, sp_lds1(sm, st.a_prev), sp_lds1(sm, o - 8u),
+                                                 sp_lds1(sm, st.a_next), uo, c, p.st);
         if (p.post == POST_INJECT) {
-            const long kg = (long)tl.k0 + kk;
+            const long kg = (long)tl.k0 + st.kk;
             p.crhs[(long)(q >> 1) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;         // gs.cpp:283
         } else {
             st.acc += rv * rv;
         }
     }
-    if (p.post == POST_NORM2 && (st.ok & 2u)) {          // odd column 2kg+1
-        const Coef4 c = Arith<ARITH>::coef(sm.V1[o], sm.V2[o], p.st);
-        const double rv = Arith<ARITH>::residual(sm.F[o], uo, sm.U[bu + p.SWK + kk], ue, sm.U[bd + p.SWK + kk],
-                                                 sm.U[e + 1], c, p.st);
+    if (st.ok_cur & 2u) {                                // odd column 2kg+1 (POST_NORM2 only)
+        const Coef4 c = Arith<ARITH>::coef(sp_lds1(sm, o + 2u * geo.ringb), sp_lds1(sm, o + 3u * geo.ringb), p.st);
+        const double rv = Arith<ARITH>::residual(sp_lds1(sm, o + geo.ringb), uo, sp_lds1(sm, st.a_prev + geo.swkb), ue,
+                                                 sp_lds1(sm, st.a_next + geo.swkb), sp_lds1(sm, e + 8u), c, p.st);
         st.acc += rv * rv;
     }
 }
@@ -390,45 +427,49 @@ SP_FN void producer_prologue(const Params& p, const Tile& tl, const Smem& sm)
     for (int g = 0; g < 2 && g < ng; ++g) issue_group_loads(p, tl, sm, g);
 }
 
-// wait until the first group has landed (every thread, before the first step)
-SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
-// after wait_first_row: the stage warps' operand fetch for the very first step
-SP_FN void first_prefetch(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st)
+SP_FN void producer_step(const Params& p, const Tile& tl, const Smem& sm, int t)
 {
-    if (st.role == ROLE_STAGE) stage_prefetch(p, tl, sm, st);
+    const int q = t - 4 * p.K - 1;                      // finished by the previous step
+    if (p.write_u && q >= tl.rb0 && q <= tl.rb1) issue_row_store(p, tl, sm, q);
+    // group g is requested LEAD steps before its first row: its ring slots were last read (row
+    // t-4K-3 and older) in the previous step
+    const int d = t + LEAD - tl.R0;
+    if (d % GROUP == 0 && d / GROUP >= 2 && d / GROUP < num_groups(tl)) {
+        sp_store_wait_read2();                          // the slots' previous rows have left shared memory
+        issue_group_loads(p, tl, sm, d / GROUP);
+    }
 }
 
-// everything a thread does in step t; a block barrier separates consecutive steps.  On entry row
-// t has landed (awaited at the end of the previous step).
-template <int ARITH>
-SP_FN void thread_step(const Params& p, const Tile& tl, const Smem& sm, ThreadState& st, int t, int lane)
+// wait until the first group has landed (every thread, before the first step)
+SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
+
+// the role's work of step t (on entry row t has landed: awaited at the end of the previous step)
+template <int ARITH, int NG>
+SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t, int lane)
 {
-    if (st.role == ROLE_PRODUCER) {
-        if (lane == 0) {
-            const int q = t - 4 * p.K - 1;              // finished by the previous step
-            if (p.write_u && q >= tl.rb0 && q <= tl.rb1) issue_row_store(p, tl, sm, q);
-            // group g is requested LEAD steps before its first row: its ring slots were last read
-            // (row t-4K-3 and older) in the previous step
-            const int d = t + LEAD - tl.R0;
-            if (d % GROUP == 0 && d / GROUP >= 2 && d / GROUP < num_groups(tl)) {
-                sp_store_wait_read2();                  // the slots' previous rows have left shared memory
-                issue_group_loads(p, tl, sm, d / GROUP);
-            }
-        }
-    } else if (st.role == ROLE_STAGE) {
-        stage_row<ARITH>(p, tl, sm, st);
+    if (st.role == ROLE_STAGE) {
+        if (st.par) stage_step<ARITH, NG, 1>(p, geo, sm, st);
+        else stage_step<ARITH, NG, 0>(p, geo, sm, st);
         // the last stage's rows go to the bulk-store engine next step: generic -> async proxy
         if (st.idx == 2 * p.K - 1) sp_fence_async();
+        const unsigned o = st.ok_cur; st.ok_cur = st.ok_nxt; st.ok_nxt = o;
+        st.par ^= 1;
     } else if (st.role == ROLE_PRE) {
-        prolong_row(p, tl, sm, st);
+        pre_step(p, tl, geo, sm, st);
         if (p.K == 0) sp_fence_async();
-    } else {
-        post_row<ARITH>(p, tl, sm, st);
+    } else if (st.role == ROLE_POST) {
+        post_step<ARITH>(p, tl, geo, sm, st);
+    } else if (lane == 0) {
+        producer_step(p, tl, sm, t);
     }
+}
+
+// end of step t: advance the row pointers; row t+1 must have landed before anyone touches it in
+// step t+1, so wait whenever it opens a new group.  (A block barrier follows.)
+SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t)
+{
     st.row += 1;
-    st.base = ring_next(p, st.base);
-    if (st.role == ROLE_STAGE) stage_prefetch(p, tl, sm, st);
-    // row t+1 must have landed before anyone touches it in step t+1: wait when it opens a new group
+    st.a_prev = st.a_cur; st.a_cur = st.a_next; st.a_next = ring_adv(st.a_next, geo, st.lim);
     st.wphase += 1;
     if (st.wphase == GROUP) {
         st.wphase = 0;

@@ -54,6 +54,10 @@ SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes) { std
 SP_FN void sp_store_commit() {}
 SP_FN void sp_store_wait_read2() {}
 SP_FN void sp_fence_async() {}
+SP_FN D2 sp_lds2(const Smem& sm, unsigned off) { return *reinterpret_cast<const D2*>(sm.raw + off); }
+SP_FN double sp_lds1(const Smem& sm, unsigned off) { return *reinterpret_cast<const double*>(sm.raw + off); }
+SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v) { *reinterpret_cast<D2*>(sm.raw + off) = v; }
+SP_FN void sp_sts1(const Smem& sm, unsigned off, double v) { *reinterpret_cast<double*>(sm.raw + off) = v; }
 }  // namespace sp
 }  // namespace mgb200
 
@@ -105,10 +109,10 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
         carve(sm, smem.data(), p.SWK);
         const Tile tl = make_tile(p, tile);
         producer_prologue(p, tl, sm);
+        const Geo geo = make_geo(p);
         std::vector<ThreadState> st(THREADS);
-        for (int tid = 0; tid < THREADS; ++tid) st[tid] = init_thread(p, tl, tid);
+        for (int tid = 0; tid < THREADS; ++tid) st[tid] = init_thread(p, tl, geo, tid);
         wait_first_row(sm);
-        for (int tid = 0; tid < THREADS; ++tid) first_prefetch(p, tl, sm, st[tid]);
         const int t1 = last_step(p, tl);
         for (int t = first_step(tl); t <= t1; ++t) {
             std::iota(perm.begin(), perm.end(), 0);
@@ -120,8 +124,15 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
                 }
             for (int q = 0; q < THREADS; ++q) {
                 const int tid = perm[q];
-                if (arith == MGB200_ARITH_EXACT) thread_step<MGB200_ARITH_EXACT>(p, tl, sm, st[tid], t, tid & 31);
-                else thread_step<MGB200_ARITH_FAST>(p, tl, sm, st[tid], t, tid & 31);
+                const int lane = tid & 31;
+                if (arith == MGB200_ARITH_EXACT) {
+                    if (p.SWK > 64) role_step<MGB200_ARITH_EXACT, 2>(p, tl, geo, sm, st[tid], t, lane);
+                    else role_step<MGB200_ARITH_EXACT, 1>(p, tl, geo, sm, st[tid], t, lane);
+                } else {
+                    if (p.SWK > 64) role_step<MGB200_ARITH_FAST, 2>(p, tl, geo, sm, st[tid], t, lane);
+                    else role_step<MGB200_ARITH_FAST, 1>(p, tl, geo, sm, st[tid], t, lane);
+                }
+                end_step(tl, geo, sm, st[tid], t);
             }
         }
         if (post == POST_NORM2) {
