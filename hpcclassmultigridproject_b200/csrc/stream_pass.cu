@@ -81,19 +81,19 @@ SP_FN void sp_sts1(const Smem& sm, unsigned off, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm.base32 + off), "d"(v) : "memory");
 }
 
-template <int ARITH, int NG>
+template <int ARITH>
 __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int lane)
 {
     const int t1 = last_step(p, tl);
     for (int t = first_step(tl); t <= t1; ++t) {
-        role_step<ARITH, NG>(p, tl, geo, sm, st, t, lane);
+        role_step<ARITH>(p, tl, geo, sm, st, t, lane);
         end_step(tl, geo, sm, st, t);
         __syncthreads();
     }
 }
 
 template <int ARITH>
-__global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double scratch[32];
@@ -113,8 +113,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_stream_pass(const __grid_constan
     if (tid == PRODUCER_WARP * 32) producer_prologue(p, tl, sm);
     ThreadState st = init_thread(p, tl, geo, tid);
     wait_first_row(sm);
-    if (p.SWK > 64) run_tile<ARITH, 2>(p, tl, geo, sm, st, lane);
-    else run_tile<ARITH, 1>(p, tl, geo, sm, st, lane);
+    run_tile<ARITH>(p, tl, geo, sm, st, lane);
     if (tid == PRODUCER_WARP * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.post == POST_NORM2) {
         const double tot = block_sum(st.acc, scratch);

@@ -14,9 +14,10 @@
 // Redundant work: HK halo pairs per strip side, 2K+1 halo rows per band side (recomputed, never
 // stored); tiles write to u_out != u_in, so no tile ever sees another tile's results.
 //
-// Warp roles (13 warps): 6 stage warps (one half-sweep each, 4 nodes per lane as two 16-byte
-// vectors), 2 prolongation warps, 4 residual-epilogue warps, 1 producer warp (one lane drives the
-// TMA engine).  Per-thread state that advances by one row per step (ring slots, rows) is kept
+// Warp roles (19 warps): 12 stage warps (two per half-sweep, 2 nodes per lane as one 16-byte
+// vector), 2 prolongation warps, 4 residual-epilogue warps, 1 producer warp (one lane drives the
+// TMA engine).  A warp's step is an almost serial dependency chain (address -> LDS -> 6 dependent
+// FP64 operations -> STS), so the block is wide (many short chains) rather than deep.  Per-thread state that advances by one row per step (ring slots, rows) is kept
 // incrementally, so a step has no division and almost no address arithmetic.
 //
 // Loads are 3-D TMA tensor copies: one instruction brings GROUP rows x both parity runs x SWK pairs
@@ -46,7 +47,8 @@ constexpr int LEAD = 5;        // a group is requested LEAD steps before its fir
 constexpr int CROWS = 3;       // coarse rows travelling with a group of fine rows
 constexpr int CW_MAX = SWK_MAX / 2 + 8;   // doubles per coarse parity run in smem
 constexpr int KMAX = 3;
-constexpr int NSTAGE = 2 * KMAX;
+constexpr int NSTW = 2;        // warps per half-sweep stage (64 pairs each)
+constexpr int NSTAGE = 2 * KMAX * NSTW;
 constexpr int NPRE = 2;        // prolongation warps (64 pairs each)
 constexpr int NPOST = 4;       // residual-epilogue warps (32 pairs each)
 constexpr int WARPS = NSTAGE + NPRE + NPOST + 1;
@@ -236,7 +238,7 @@ struct ThreadState {
     int wgroup;         // its group slot
     unsigned wpar;      // and that barrier's phase parity
     double acc;         // POST_NORM2 accumulator
-    D2 pf[2][3];        // stage: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
+    D2 pf[3];           // stage: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -262,8 +264,8 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
     s.lo = 1; s.hi = 0;                                  // empty range
     int off = 0;                                         // role row = t - off
     if (warp < NSTAGE) {
-        s.role = ROLE_STAGE; s.idx = warp; s.kk = 2 * lane; off = 2 + 2 * warp;
-        if (warp < 2 * p.K) { s.lo = tl.R0 + 1; s.hi = tl.R1 - 1; }        // rows row-1, row+1 must be staged
+        s.role = ROLE_STAGE; s.idx = warp / NSTW; s.kk = 64 * (warp % NSTW) + 2 * lane; off = 2 + 2 * s.idx;
+        if (s.idx < 2 * p.K && s.kk < p.SWK) { s.lo = tl.R0 + 1; s.hi = tl.R1 - 1; }   // rows row-1, row+1 must be staged
     } else if (warp < NSTAGE + NPRE) {
         s.role = ROLE_PRE; s.idx = warp - NSTAGE; s.kk = 64 * s.idx + 2 * lane; off = 0;
         for (int e = 0; e < 2; ++e) {
@@ -290,11 +292,10 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
     s.a_prev = (slot == 0 ? (unsigned)(RING - 1) : (unsigned)(slot - 1)) * geo.rowb + (unsigned)s.kk * 8u;
     if (s.role == ROLE_STAGE) {
         s.par = (s.idx + s.row) & 1;
-        for (int g = 0; g < 2; ++g)
-            for (int e = 0; e < 2; ++e) {
-                if (target_ok(p, tl, s.kk + 64 * g + e, s.par)) s.ok_cur |= 1u << (g * 2 + e);
-                if (target_ok(p, tl, s.kk + 64 * g + e, s.par ^ 1)) s.ok_nxt |= 1u << (g * 2 + e);
-            }
+        for (int e = 0; e < 2; ++e) {
+            if (target_ok(p, tl, s.kk + e, s.par)) s.ok_cur |= 1u << e;
+            if (target_ok(p, tl, s.kk + e, s.par ^ 1)) s.ok_nxt |= 1u << e;
+        }
     }
     s.wphase = 0; s.wgroup = 0; s.wpar = 0;
     return s;
@@ -305,55 +306,41 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 // never change, the row landed long ago (row t-1-2s at step t), and the loads then overlap the
 // barrier wait instead of sitting on the critical path of the next step.  PARN = parity of the
 // colour in that next row.
-template <int NG, int PARN>
+template <int PARN>
 SP_FN void stage_prefetch(const Geo& geo, const Smem& sm, ThreadState& st)
 {
     if (st.row + 1 < st.lo || st.row + 1 > st.hi) return;
     const unsigned b = st.a_next + (PARN ? geo.swkb : 0u) + geo.ringb;
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        st.pf[g][0] = sp_lds2(sm, b + 512u * g);
-        st.pf[g][1] = sp_lds2(sm, b + geo.ringb + 512u * g);
-        st.pf[g][2] = sp_lds2(sm, b + 2u * geo.ringb + 512u * g);
-    }
+    st.pf[0] = sp_lds2(sm, b);
+    st.pf[1] = sp_lds2(sm, b + geo.ringb);
+    st.pf[2] = sp_lds2(sm, b + 2u * geo.ringb);
 }
 
-// One half-sweep stage on row st.row (colour = stage & 1), NG 16-byte vectors per lane, PAR = the
+// One half-sweep stage on row st.row (colour = stage & 1), one 16-byte vector per lane, PAR = the
 // column parity of the colour in this row.  With pair index kk even, the horizontal neighbours of
 // targets (kk, kk+1) are three consecutive nodes of the OTHER run: from kk-1 (even columns:
 // O[kk-1], O[kk], O[kk+1]) or from kk (odd columns: E[kk], E[kk+1], E[kk+2]).
-template <int ARITH, int NG, int PAR>
+template <int ARITH, int PAR>
 SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     if (st.row >= st.lo && st.row <= st.hi) {
         const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            const unsigned go = 512u * g;
-            const D2 up = sp_lds2(sm, st.a_prev + po + go), dn = sp_lds2(sm, st.a_next + po + go);
-            double n0, n1, n2;
-            if (PAR == 0) {
-                n0 = sp_lds1(sm, st.a_cur + oo + go - 8u);
-                const D2 m = sp_lds2(sm, st.a_cur + oo + go);
-                n1 = m.x; n2 = m.y;
-            } else {
-                const D2 m = sp_lds2(sm, st.a_cur + oo + go);
-                n0 = m.x; n1 = m.y;
-                n2 = sp_lds1(sm, st.a_cur + oo + go + 16u);
-            }
-            const D2 f = st.pf[g][0], w1 = st.pf[g][1], w2 = st.pf[g][2];
-            const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
-            const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
-            D2 out;
-            out.x = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
-            out.y = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
-            const unsigned okg = (st.ok_cur >> (2 * g)) & 3u;
-            if (okg == 3u) sp_sts2(sm, st.a_cur + po + go, out);
-            else if (okg == 1u) sp_sts1(sm, st.a_cur + po + go, out.x);
-            else if (okg == 2u) sp_sts1(sm, st.a_cur + po + go + 8u, out.y);
-        }
+        const D2 up = sp_lds2(sm, st.a_prev + po), dn = sp_lds2(sm, st.a_next + po);
+        const D2 m = sp_lds2(sm, st.a_cur + oo);
+        const double x = sp_lds1(sm, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
+        const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
+        const D2 f = st.pf[0], w1 = st.pf[1], w2 = st.pf[2];
+        const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
+        const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
+        D2 out;
+        out.x = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
+        out.y = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
+        const unsigned okg = st.ok_cur & 3u;
+        if (okg == 3u) sp_sts2(sm, st.a_cur + po, out);
+        else if (okg == 1u) sp_sts1(sm, st.a_cur + po, out.x);
+        else if (okg == 2u) sp_sts1(sm, st.a_cur + po + 8u, out.y);
     }
-    stage_prefetch<NG, PAR ^ 1>(geo, sm, st);
+    stage_prefetch<PAR ^ 1>(geo, sm, st);
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
@@ -444,12 +431,12 @@ SP_FN void producer_step(const Params& p, const Tile& tl, const Smem& sm, int t)
 SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
 
 // the role's work of step t (on entry row t has landed: awaited at the end of the previous step)
-template <int ARITH, int NG>
+template <int ARITH>
 SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t, int lane)
 {
     if (st.role == ROLE_STAGE) {
-        if (st.par) stage_step<ARITH, NG, 1>(p, geo, sm, st);
-        else stage_step<ARITH, NG, 0>(p, geo, sm, st);
+        if (st.par) stage_step<ARITH, 1>(p, geo, sm, st);
+        else stage_step<ARITH, 0>(p, geo, sm, st);
         // the last stage's rows go to the bulk-store engine next step: generic -> async proxy
         if (st.idx == 2 * p.K - 1) sp_fence_async();
         const unsigned o = st.ok_cur; st.ok_cur = st.ok_nxt; st.ok_nxt = o;
@@ -486,8 +473,8 @@ SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState&
 // band count for the cheapest plan.
 struct Plan { int WK, SWK, nstrips, nbands; long RBAND; };
 
-// resident tiles per SM for a strip width (shared memory is the limit; 227 KB per SM)
-inline int tiles_per_sm(int swk) { const int k = (int)(232448 / (smem_bytes(swk) + 1024)); return k < 1 ? 1 : (k > 2 ? 2 : k); }
+// resident tiles per SM: one (608 threads x ~90 registers fill the register file)
+inline int tiles_per_sm(int) { return 1; }
 
 inline Plan make_plan(long n, int K, int sms, int force_swk = 0)
 {

@@ -125,13 +125,8 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
             for (int q = 0; q < THREADS; ++q) {
                 const int tid = perm[q];
                 const int lane = tid & 31;
-                if (arith == MGB200_ARITH_EXACT) {
-                    if (p.SWK > 64) role_step<MGB200_ARITH_EXACT, 2>(p, tl, geo, sm, st[tid], t, lane);
-                    else role_step<MGB200_ARITH_EXACT, 1>(p, tl, geo, sm, st[tid], t, lane);
-                } else {
-                    if (p.SWK > 64) role_step<MGB200_ARITH_FAST, 2>(p, tl, geo, sm, st[tid], t, lane);
-                    else role_step<MGB200_ARITH_FAST, 1>(p, tl, geo, sm, st[tid], t, lane);
-                }
+                if (arith == MGB200_ARITH_EXACT) role_step<MGB200_ARITH_EXACT>(p, tl, geo, sm, st[tid], t, lane);
+                else role_step<MGB200_ARITH_FAST>(p, tl, geo, sm, st[tid], t, lane);
                 end_step(tl, geo, sm, st[tid], t);
             }
         }
