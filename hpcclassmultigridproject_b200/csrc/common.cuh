@@ -119,6 +119,17 @@ struct Arith<MGB200_ARITH_EXACT> {
         t = __dsub_rn(t, __dmul_rn(k.b, rt));
         return __ddiv_rn(t, s.diag);
     }
+    // the same update split in two: head = (rhs - c*up) - a*lf ; tail = ((head - d*dn) - b*rt) / diag
+    static __device__ __forceinline__ double gs_head(double rhs, double up, double lf, const Coef4& k)
+    {
+        return __dsub_rn(__dsub_rn(rhs, __dmul_rn(k.c, up)), __dmul_rn(k.a, lf));
+    }
+    static __device__ __forceinline__ double gs_tail(double t, double dn, double rt, double kd, double kb, const Stencil& s)
+    {
+        t = __dsub_rn(t, __dmul_rn(kd, dn));
+        t = __dsub_rn(t, __dmul_rn(kb, rt));
+        return __ddiv_rn(t, s.diag);
+    }
     // gs.cpp:75    rhs - (diag*u + c*up + a*lf + d*dn + b*rt)
     static __device__ __forceinline__ double residual(double rhs, double u, double up, double lf, double dn,
                                                       double rt, const Coef4& k, const Stencil& s)
@@ -157,6 +168,16 @@ struct Arith<MGB200_ARITH_FAST> {
         t = fma(-k.a, lf, t);
         t = fma(-k.d, dn, t);
         t = fma(-k.b, rt, t);
+        return t * s.inv_diag;
+    }
+    static __device__ __forceinline__ double gs_head(double rhs, double up, double lf, const Coef4& k)
+    {
+        return fma(-k.a, lf, fma(-k.c, up, rhs));
+    }
+    static __device__ __forceinline__ double gs_tail(double t, double dn, double rt, double kd, double kb, const Stencil& s)
+    {
+        t = fma(-kd, dn, t);
+        t = fma(-kb, rt, t);
         return t * s.inv_diag;
     }
     static __device__ __forceinline__ double residual(double rhs, double u, double up, double lf, double dn,

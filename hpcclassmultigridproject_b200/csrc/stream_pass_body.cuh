@@ -238,7 +238,9 @@ struct ThreadState {
     int wgroup;         // its group slot
     unsigned wpar;      // and that barrier's phase parity
     double acc;         // POST_NORM2 accumulator
-    D2 pf[3];           // stage: rhs, v1, v2 of the NEXT row's targets, fetched before the barrier
+    // stage: everything of the NEXT row's update that does not depend on the row below it, computed
+    // before the step barrier: partial sums, the two coefficients still needed, the right neighbours
+    double h0, h1, kd0, kd1, kb0, kb1, rt0, rt1;
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -302,45 +304,52 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 }
 
 // ------------------------------------------------------------------------------------------
-// Stage warps fetch rhs, v1, v2 of their NEXT row's targets before the step barrier: those fields
-// never change, the row landed long ago (row t-1-2s at step t), and the loads then overlap the
-// barrier wait instead of sitting on the critical path of the next step.  PARN = parity of the
-// colour in that next row.
-template <int PARN>
-SP_FN void stage_prefetch(const Geo& geo, const Smem& sm, ThreadState& st)
+// Stage warps split the update of a node in two (Arith::gs_head / gs_tail).  Of the operands of
+// row i at step t only the row below (i+1) was written during step t-1; the row above, the
+// horizontal neighbours, rhs and the velocities are older.  So at the END of step t-1, before the
+// block barrier, a warp loads all of those for its next row and computes the coefficients and the
+// partial sum (rhs - c*up) - a*lf; after the barrier only one vector load, two FMAs and the scale
+// remain on the critical path.  PARN = column parity of the colour in that next row.
+// With pair index kk even, the horizontal neighbours of targets (kk, kk+1) are three consecutive
+// nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd columns:
+// E[kk], E[kk+1], E[kk+2]).
+template <int ARITH, int PARN>
+SP_FN void stage_head(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     if (st.row + 1 < st.lo || st.row + 1 > st.hi) return;
-    const unsigned b = st.a_next + (PARN ? geo.swkb : 0u) + geo.ringb;
-    st.pf[0] = sp_lds2(sm, b);
-    st.pf[1] = sp_lds2(sm, b + geo.ringb);
-    st.pf[2] = sp_lds2(sm, b + 2u * geo.ringb);
+    const unsigned pn = PARN ? geo.swkb : 0u, on = PARN ? 0u : geo.swkb;
+    const unsigned b = st.a_next + pn + geo.ringb;
+    const D2 f = sp_lds2(sm, b), w1 = sp_lds2(sm, b + geo.ringb), w2 = sp_lds2(sm, b + 2u * geo.ringb);
+    const D2 up = sp_lds2(sm, st.a_cur + pn);             // the current row is the next row's upper neighbour
+    const D2 m = sp_lds2(sm, st.a_next + on);
+    const double x = sp_lds1(sm, st.a_next + on + (PARN ? 16u : 0u) - (PARN ? 0u : 8u));
+    const double n0 = PARN ? m.x : x, n1 = PARN ? m.y : m.x, n2 = PARN ? x : m.y;
+    const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
+    const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
+    st.h0 = Arith<ARITH>::gs_head(f.x, up.x, n0, c0);
+    st.h1 = Arith<ARITH>::gs_head(f.y, up.y, n1, c1);
+    st.kd0 = c0.d; st.kb0 = c0.b; st.kd1 = c1.d; st.kb1 = c1.b;
+    st.rt0 = n1; st.rt1 = n2;
 }
 
 // One half-sweep stage on row st.row (colour = stage & 1), one 16-byte vector per lane, PAR = the
-// column parity of the colour in this row.  With pair index kk even, the horizontal neighbours of
-// targets (kk, kk+1) are three consecutive nodes of the OTHER run: from kk-1 (even columns:
-// O[kk-1], O[kk], O[kk+1]) or from kk (odd columns: E[kk], E[kk+1], E[kk+2]).
+// column parity of the colour in this row: finish the update prepared by stage_head, then prepare
+// the next row.
 template <int ARITH, int PAR>
 SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     if (st.row >= st.lo && st.row <= st.hi) {
-        const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
-        const D2 up = sp_lds2(sm, st.a_prev + po), dn = sp_lds2(sm, st.a_next + po);
-        const D2 m = sp_lds2(sm, st.a_cur + oo);
-        const double x = sp_lds1(sm, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
-        const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
-        const D2 f = st.pf[0], w1 = st.pf[1], w2 = st.pf[2];
-        const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
-        const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
+        const unsigned po = PAR ? geo.swkb : 0u;
+        const D2 dn = sp_lds2(sm, st.a_next + po);
         D2 out;
-        out.x = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
-        out.y = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
+        out.x = Arith<ARITH>::gs_tail(st.h0, dn.x, st.rt0, st.kd0, st.kb0, p.st);
+        out.y = Arith<ARITH>::gs_tail(st.h1, dn.y, st.rt1, st.kd1, st.kb1, p.st);
         const unsigned okg = st.ok_cur & 3u;
         if (okg == 3u) sp_sts2(sm, st.a_cur + po, out);
         else if (okg == 1u) sp_sts1(sm, st.a_cur + po, out.x);
         else if (okg == 2u) sp_sts1(sm, st.a_cur + po + 8u, out.y);
     }
-    stage_prefetch<PAR ^ 1>(geo, sm, st);
+    stage_head<ARITH, PAR ^ 1>(p, geo, sm, st);
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
