@@ -81,14 +81,75 @@ SP_FN void sp_sts1(const Smem& sm, unsigned off, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(sm.base32 + off), "d"(v) : "memory");
 }
 
+// the per-step block barrier, reached from role-specific code (same barrier resource, any PC)
+__device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// Role-specialised step loops.  All roles execute exactly one block barrier per step, t = R0 .. t1.
+// The loops are unrolled by GROUP (= 4) steps so that the wait for the next TMA group sits at a
+// fixed place and, for the stage warps, the column parity of every step is a compile-time
+// constant: a step is a serial dependency chain and every branch in it is pure latency.
+template <int ARITH, int P0>
+__device__ __forceinline__ void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
+{
+    const bool feeds_store = (st.idx == 2 * p.K - 1);   // its rows go to the bulk-store engine: generic -> async proxy
+    const int t1 = last_step(p, tl);
+    int t = first_step(tl);
+    for (; t + 3 <= t1; t += 4) {
+        stage_step<ARITH, P0>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        advance_row(geo, st);
+        step_barrier();
+        stage_step<ARITH, P0 ^ 1>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        advance_row(geo, st);
+        step_barrier();
+        stage_step<ARITH, P0>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        advance_row(geo, st);
+        step_barrier();
+        stage_step<ARITH, P0 ^ 1>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        advance_row(geo, st);
+        wait_group(tl, sm, st, t + 3);
+        step_barrier();
+    }
+    st.par = P0;
+    for (; t <= t1; ++t) {
+        if (st.par) stage_step<ARITH, 1>(p, geo, sm, st); else stage_step<ARITH, 0>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        stage_flip(st);
+        end_step(tl, geo, sm, st, t);
+        step_barrier();
+    }
+}
+
+template <class Work>
+__device__ __forceinline__ void role_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, Work work)
+{
+    const int t1 = last_step(p, tl);
+    int t = first_step(tl);
+    for (; t + 3 <= t1; t += 4) {
+        work(t); advance_row(geo, st); step_barrier();
+        work(t + 1); advance_row(geo, st); step_barrier();
+        work(t + 2); advance_row(geo, st); step_barrier();
+        work(t + 3); advance_row(geo, st); wait_group(tl, sm, st, t + 3); step_barrier();
+    }
+    for (; t <= t1; ++t) { work(t); end_step(tl, geo, sm, st, t); step_barrier(); }
+}
+
 template <int ARITH>
 __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int lane)
 {
-    const int t1 = last_step(p, tl);
-    for (int t = first_step(tl); t <= t1; ++t) {
-        role_step<ARITH>(p, tl, geo, sm, st, t, lane);
-        end_step(tl, geo, sm, st, t);
-        __syncthreads();
+    if (st.role == ROLE_STAGE) {
+        if (st.par) stage_loop<ARITH, 1>(p, tl, geo, sm, st);
+        else stage_loop<ARITH, 0>(p, tl, geo, sm, st);
+    } else if (st.role == ROLE_PRE) {
+        role_loop(p, tl, geo, sm, st, [&](int) { pre_step(p, tl, geo, sm, st); if (p.K == 0) sp_fence_async(); });
+    } else if (st.role == ROLE_POST) {
+        role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH>(p, tl, geo, sm, st); });
+    } else {
+        role_loop(p, tl, geo, sm, st, [&](int t) { if (lane == 0) producer_step(p, tl, sm, t); });
     }
 }
 

@@ -231,16 +231,13 @@ struct ThreadState {
     int lo, hi;         // rows on which the role acts: [lo, hi]
     unsigned a_prev, a_cur, a_next;   // offsets of even-run element kk of rows row-1, row, row+1
     unsigned lim;       // ringb + kk*8: wrap limit of those offsets
-    unsigned ok_cur;    // validity bits for this step's column parity (stage) / role specific
-    unsigned ok_nxt;    // stage: validity bits for the next step's parity
+    unsigned ok_cur;    // pre / post: validity bits of the lane's nodes
+    unsigned okp[2];    // stage: validity bits of the lane's two targets for column parity 0 / 1
     int par;            // stage: column parity of the colour in `row`
     int wphase;         // (row awaited at the end of the step - R0) mod GROUP
     int wgroup;         // its group slot
     unsigned wpar;      // and that barrier's phase parity
     double acc;         // POST_NORM2 accumulator
-    // stage: everything of the NEXT row's update that does not depend on the row below it, computed
-    // before the step barrier: partial sums, the two coefficients still needed, the right neighbours
-    double h0, h1, kd0, kd1, kb0, kb1, rt0, rt1;
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -262,7 +259,7 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 {
     ThreadState s;
     const int warp = tid >> 5, lane = tid & 31;
-    s.acc = 0.0; s.ok_cur = 0; s.ok_nxt = 0; s.idx = 0; s.kk = 0; s.par = 0;
+    s.acc = 0.0; s.ok_cur = 0; s.okp[0] = s.okp[1] = 0; s.idx = 0; s.kk = 0; s.par = 0;
     s.lo = 1; s.hi = 0;                                  // empty range
     int off = 0;                                         // role row = t - off
     if (warp < NSTAGE) {
@@ -294,62 +291,39 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
     s.a_prev = (slot == 0 ? (unsigned)(RING - 1) : (unsigned)(slot - 1)) * geo.rowb + (unsigned)s.kk * 8u;
     if (s.role == ROLE_STAGE) {
         s.par = (s.idx + s.row) & 1;
-        for (int e = 0; e < 2; ++e) {
-            if (target_ok(p, tl, s.kk + e, s.par)) s.ok_cur |= 1u << e;
-            if (target_ok(p, tl, s.kk + e, s.par ^ 1)) s.ok_nxt |= 1u << e;
-        }
+        for (int e = 0; e < 2; ++e)
+            for (int par = 0; par < 2; ++par)
+                if (target_ok(p, tl, s.kk + e, par)) s.okp[par] |= 1u << e;
     }
     s.wphase = 0; s.wgroup = 0; s.wpar = 0;
     return s;
 }
 
 // ------------------------------------------------------------------------------------------
-// Stage warps split the update of a node in two (Arith::gs_head / gs_tail).  Of the operands of
-// row i at step t only the row below (i+1) was written during step t-1; the row above, the
-// horizontal neighbours, rhs and the velocities are older.  So at the END of step t-1, before the
-// block barrier, a warp loads all of those for its next row and computes the coefficients and the
-// partial sum (rhs - c*up) - a*lf; after the barrier only one vector load, two FMAs and the scale
-// remain on the critical path.  PARN = column parity of the colour in that next row.
+// One half-sweep stage on row st.row (colour = stage & 1), one 16-byte vector per lane, PAR = the
+// column parity of the colour in this row.  Branch-free: operands are always loaded (every offset
+// stays inside the ring) and only the two stores are predicated, because a warp's step is a serial
+// dependency chain in which every taken or not-taken branch costs more than the arithmetic.
 // With pair index kk even, the horizontal neighbours of targets (kk, kk+1) are three consecutive
-// nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd columns:
-// E[kk], E[kk+1], E[kk+2]).
-template <int ARITH, int PARN>
-SP_FN void stage_head(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
+// nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd
+// columns: E[kk], E[kk+1], E[kk+2]).
+template <int ARITH, int PAR>
+SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, const ThreadState& st)
 {
-    if (st.row + 1 < st.lo || st.row + 1 > st.hi) return;
-    const unsigned pn = PARN ? geo.swkb : 0u, on = PARN ? 0u : geo.swkb;
-    const unsigned b = st.a_next + pn + geo.ringb;
-    const D2 f = sp_lds2(sm, b), w1 = sp_lds2(sm, b + geo.ringb), w2 = sp_lds2(sm, b + 2u * geo.ringb);
-    const D2 up = sp_lds2(sm, st.a_cur + pn);             // the current row is the next row's upper neighbour
-    const D2 m = sp_lds2(sm, st.a_next + on);
-    const double x = sp_lds1(sm, st.a_next + on + (PARN ? 16u : 0u) - (PARN ? 0u : 8u));
-    const double n0 = PARN ? m.x : x, n1 = PARN ? m.y : m.x, n2 = PARN ? x : m.y;
+    const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
+    const unsigned c = st.a_cur + po;
+    const D2 up = sp_lds2(sm, st.a_prev + po), dn = sp_lds2(sm, st.a_next + po);
+    const D2 m = sp_lds2(sm, st.a_cur + oo);
+    const double x = sp_lds1(sm, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
+    const D2 f = sp_lds2(sm, c + geo.ringb), w1 = sp_lds2(sm, c + 2u * geo.ringb), w2 = sp_lds2(sm, c + 3u * geo.ringb);
+    const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
     const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
     const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
-    st.h0 = Arith<ARITH>::gs_head(f.x, up.x, n0, c0);
-    st.h1 = Arith<ARITH>::gs_head(f.y, up.y, n1, c1);
-    st.kd0 = c0.d; st.kb0 = c0.b; st.kd1 = c1.d; st.kb1 = c1.b;
-    st.rt0 = n1; st.rt1 = n2;
-}
-
-// One half-sweep stage on row st.row (colour = stage & 1), one 16-byte vector per lane, PAR = the
-// column parity of the colour in this row: finish the update prepared by stage_head, then prepare
-// the next row.
-template <int ARITH, int PAR>
-SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
-{
-    if (st.row >= st.lo && st.row <= st.hi) {
-        const unsigned po = PAR ? geo.swkb : 0u;
-        const D2 dn = sp_lds2(sm, st.a_next + po);
-        D2 out;
-        out.x = Arith<ARITH>::gs_tail(st.h0, dn.x, st.rt0, st.kd0, st.kb0, p.st);
-        out.y = Arith<ARITH>::gs_tail(st.h1, dn.y, st.rt1, st.kd1, st.kb1, p.st);
-        const unsigned okg = st.ok_cur & 3u;
-        if (okg == 3u) sp_sts2(sm, st.a_cur + po, out);
-        else if (okg == 1u) sp_sts1(sm, st.a_cur + po, out.x);
-        else if (okg == 2u) sp_sts1(sm, st.a_cur + po + 8u, out.y);
-    }
-    stage_head<ARITH, PAR ^ 1>(p, geo, sm, st);
+    const double o0 = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
+    const double o1 = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
+    const bool act = st.row >= st.lo && st.row <= st.hi;
+    if (act && (st.okp[PAR] & 1u)) sp_sts1(sm, c, o0);
+    if (act && (st.okp[PAR] & 2u)) sp_sts1(sm, c + 8u, o1);
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
@@ -439,6 +413,9 @@ SP_FN void producer_step(const Params& p, const Tile& tl, const Smem& sm, int t)
 // wait until the first group has landed (every thread, before the first step)
 SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
 
+// after a stage step: the next row has the other column parity
+SP_FN void stage_flip(ThreadState& st) { st.par ^= 1; }
+
 // the role's work of step t (on entry row t has landed: awaited at the end of the previous step)
 template <int ARITH>
 SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t, int lane)
@@ -448,8 +425,7 @@ SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
         else stage_step<ARITH, 0>(p, geo, sm, st);
         // the last stage's rows go to the bulk-store engine next step: generic -> async proxy
         if (st.idx == 2 * p.K - 1) sp_fence_async();
-        const unsigned o = st.ok_cur; st.ok_cur = st.ok_nxt; st.ok_nxt = o;
-        st.par ^= 1;
+        stage_flip(st);
     } else if (st.role == ROLE_PRE) {
         pre_step(p, tl, geo, sm, st);
         if (p.K == 0) sp_fence_async();
@@ -462,10 +438,23 @@ SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
 
 // end of step t: advance the row pointers; row t+1 must have landed before anyone touches it in
 // step t+1, so wait whenever it opens a new group.  (A block barrier follows.)
-SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t)
+SP_FN void advance_row(const Geo& geo, ThreadState& st)
 {
     st.row += 1;
     st.a_prev = st.a_cur; st.a_cur = st.a_next; st.a_next = ring_adv(st.a_next, geo, st.lim);
+}
+
+// called after the LAST step of a group (the step whose successor opens group `next_group`)
+SP_FN void wait_group(const Tile& tl, const Smem& sm, ThreadState& st, int t)
+{
+    st.wgroup += 1;
+    if (st.wgroup == NGROUP) { st.wgroup = 0; st.wpar ^= 1u; }
+    if (t + 1 <= tl.R1) sp_bar_wait(&sm.full[st.wgroup], st.wpar);
+}
+
+SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t)
+{
+    advance_row(geo, st);
     st.wphase += 1;
     if (st.wphase == GROUP) {
         st.wphase = 0;
