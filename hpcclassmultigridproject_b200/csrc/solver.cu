@@ -165,7 +165,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         MGB_CUDA(cudaMemsetAsync(g.v1, 0, bytes, stream));
         MGB_CUDA(cudaMemsetAsync(g.v2, 0, bytes, stream));
     }
-    partials_cap = std::max(residual_partials_count(N), stream_pass_tiles(N, -1)) + 8;
+    partials_cap = std::max(residual_partials_count(N), stream_pass_tiles(N, N + 1, -1)) + 8;
     MGB_CUDA(cudaMalloc(&d_partials, partials_cap * sizeof(double)));
     MGB_CUDA(cudaMalloc(&d_norm2, 8 * sizeof(double)));
     MGB_CUDA(cudaMemsetAsync(d_norm2, 0, 8 * sizeof(double), stream));
@@ -301,7 +301,7 @@ int mgb200_solver::record_cycle()
     if (opt.plan == MGB200_PLAN_FUSED && maxlvl > 1) {
         // the level-0 up leg already produced the per-tile sums of squares (its LAST chunk did)
         const int last_k = opt.niter == 0 ? 0 : ((opt.niter - 1) % 3) + 1;
-        MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, last_k), d_norm2, stream));
+        MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, N + 1, last_k), d_norm2, stream));
     } else {
         MGB_TRY(residual_norm_level0());
     }

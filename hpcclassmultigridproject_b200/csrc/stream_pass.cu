@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <tuple>
 
 #include "stream_pass_body.cuh"
 
@@ -207,17 +208,17 @@ static int encode_field(TensorMapStorage* out, const double* base, long odd, lon
     return MGB200_OK;
 }
 
-static const Plan& plan_for(long n, int K)
+static const Plan& plan_for(long n, long nrows, int K)
 {
-    static std::map<std::pair<long, int>, Plan> cache;
+    static std::map<std::tuple<long, long, int>, Plan> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_pair(n, K);
+    auto key = std::make_tuple(n, nrows, K);
     auto it = cache.find(key);
     if (it == cache.end()) {
         int force = 0;
         if (const char* e = getenv("MGB200_SWK")) force = atoi(e);       // tuning aid: pin the strip width
-        it = cache.emplace(key, make_plan(n, K, g_sms > 0 ? g_sms : 148, force)).first;
+        it = cache.emplace(key, make_plan(n, nrows, K, g_sms > 0 ? g_sms : 148, force)).first;
     }
     return it->second;
 }
@@ -244,15 +245,15 @@ int stream_pass_init()
     return MGB200_OK;
 }
 
-long stream_pass_tiles(long n, int iters)
+long stream_pass_tiles(long n, long nrows, int iters)
 {
     if (iters >= 0) {
-        const Plan& pl = plan_for(n, iters > KMAX ? KMAX : iters);
+        const Plan& pl = plan_for(n, nrows, iters > KMAX ? KMAX : iters);
         return (long)pl.nstrips * pl.nbands;
     }
     long m = 0;
     for (int K = 0; K <= KMAX; ++K) {
-        const Plan& pl = plan_for(n, K);
+        const Plan& pl = plan_for(n, nrows, K);
         m = std::max(m, (long)pl.nstrips * pl.nbands);
     }
     return m;
@@ -264,9 +265,15 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
     if (a.n < 8 || (a.n & 3)) return fail(MGB200_ERR_INVALID, "stream_pass: n must be a multiple of 4, >= 8");
     if (!a.L.split() || a.u_out == a.u_in) return fail(MGB200_ERR_INVALID, "stream_pass: needs the split layout and u_out != u_in");
     MGB_TRY(stream_pass_init());
-    const Plan& pl = plan_for(a.n, a.iters);
+    const bool whole = a.rows_mem == 0;
+    const long own_lo = whole ? 0 : a.own_lo, own_hi = whole ? a.n : a.own_hi;
+    const Plan& pl = plan_for(a.n, own_hi - own_lo + 1, a.iters);
     Params p{};
     p.n = a.n; p.nhalf = a.n / 2;
+    p.own_lo = own_lo; p.own_hi = own_hi;
+    p.row0 = whole ? 0 : a.row0; p.rows_mem = whole ? a.n + 1 : a.rows_mem;
+    p.mem_lo = p.row0; p.mem_hi = p.row0 + p.rows_mem - 1;
+    p.crow0 = whole ? 0 : a.crow0; p.crows_mem = whole ? a.n / 2 + 1 : a.crows_mem;
     p.pitch = a.L.pitch; p.odd = a.L.odd;
     p.cpitch = a.Lc.pitch; p.codd = a.Lc.odd;
     p.RBAND = pl.RBAND; p.WK = pl.WK; p.SWK = pl.SWK; p.nstrips = pl.nstrips; p.nbands = pl.nbands;
@@ -279,11 +286,11 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
     p.st = a.st;
     p.u_in = a.u_in; p.rhs = a.rhs; p.v1 = a.v1; p.v2 = a.v2; p.cu = a.coarse_u;
     // the u map of a zero-input pass is never dereferenced (its boxes lie out of bounds): any valid field will do
-    MGB_TRY(encode_field(&p.maps[FIELD_U], a.u_in ? a.u_in : a.rhs, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
-    MGB_TRY(encode_field(&p.maps[FIELD_F], a.rhs, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
-    MGB_TRY(encode_field(&p.maps[FIELD_V1], a.v1, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
-    MGB_TRY(encode_field(&p.maps[FIELD_V2], a.v2, a.L.odd, a.L.pitch, a.n + 1, pl.SWK, GROUP));
-    if (a.coarse_u) MGB_TRY(encode_field(&p.maps[FIELD_C], a.coarse_u, a.Lc.odd, a.Lc.pitch, a.n / 2 + 1, p.CW, CROWS));
+    MGB_TRY(encode_field(&p.maps[FIELD_U], a.u_in ? a.u_in : a.rhs, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_F], a.rhs, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_V1], a.v1, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
+    MGB_TRY(encode_field(&p.maps[FIELD_V2], a.v2, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
+    if (a.coarse_u) MGB_TRY(encode_field(&p.maps[FIELD_C], a.coarse_u, a.Lc.odd, a.Lc.pitch, p.crows_mem, p.CW, CROWS));
     p.u_out = a.u_out; p.crhs = a.coarse_rhs; p.partials = a.partials;
     if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "stream_pass: POST_INJECT without coarse_rhs");
     if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "stream_pass: POST_NORM2 without partials");

@@ -33,11 +33,15 @@ struct StreamPassArgs {
     double* coarse_rhs;     // POST_INJECT target (layout Lc)
     double* partials;       // POST_NORM2: one double per tile, stream_pass_tiles() entries
     int arith;
+    // row window (row-slab sharding).  rows_mem == 0 means "whole level": rows 0..n owned and held.
+    long own_lo, own_hi;    // rows to produce
+    long row0, rows_mem;    // fine arrays hold global rows row0 .. row0+rows_mem-1
+    long crow0, crows_mem;  // same for the coarse arrays
 };
 
 // number of tiles (= partial sums written by POST_NORM2) of a pass over level n with `iters`
 // fused iterations; iters < 0: the maximum over all iteration counts (buffer sizing)
-long stream_pass_tiles(long n, int iters);
+long stream_pass_tiles(long n, long nrows, int iters);
 // one-time attribute setup
 int stream_pass_init();
 int stream_pass(const StreamPassArgs& a, cudaStream_t s);

@@ -64,6 +64,11 @@ struct Params {
     long pitch, odd;           // split layout of this level
     long cpitch, codd;         // split layout of the next coarser level
     long RBAND;                // owned rows per band
+    // row window (row-slab sharding; a single GPU owns and holds rows 0..n):
+    long own_lo, own_hi;       // rows this launch must produce
+    long mem_lo, mem_hi;       // rows present in the arrays (own rows + halo rows received from neighbours)
+    long row0, crow0;          // global row index of memory row 0 of the fine / coarse arrays
+    long rows_mem, crows_mem;  // rows held by the fine / coarse arrays
     int WK, SWK;               // owned pairs per strip, pairs per smem row (WK + 2 HK)
     int nstrips, nbands;
     int K;                     // fused RB iterations, 0..3
@@ -128,11 +133,11 @@ SP_FN Tile make_tile(const Params& p, long tile)
     Tile tl;
     const long strip = tile % p.nstrips, band = tile / p.nstrips;
     const long HR = 2 * p.K + 1;
-    long rb0 = band * p.RBAND, rb1 = rb0 + p.RBAND - 1;
-    if (rb1 > p.n) rb1 = p.n;
+    long rb0 = p.own_lo + band * p.RBAND, rb1 = rb0 + p.RBAND - 1;
+    if (rb1 > p.own_hi) rb1 = p.own_hi;
     long R0 = rb0 - HR, R1 = rb1 + HR;
-    if (R0 < 0) R0 = 0;
-    if (R1 > p.n) R1 = p.n;
+    if (R0 < p.mem_lo) R0 = p.mem_lo;
+    if (R1 > p.mem_hi) R1 = p.mem_hi;
     tl.kb = (int)(strip * p.WK);
     tl.k0 = tl.kb - HK;
     tl.rb0 = (int)rb0; tl.rb1 = (int)rb1; tl.R0 = (int)R0; tl.R1 = (int)R1;
@@ -173,19 +178,21 @@ SP_FN void issue_group_loads(const Params& p, const Tile& tl, const Smem& sm, in
     const unsigned fine = (unsigned)(GROUP * 2 * p.SWK * 8), coarse = (unsigned)(CROWS * 2 * p.CW * 8);
     sp_bar_expect(bar, 4u * fine + (p.pre ? coarse : 0u));
     const long so = (long)gs * GROUP * 2 * p.SWK;
-    // a zero iterate is produced by a box that lies entirely below the last row
-    sp_tma_load(p, FIELD_U, sm.U + so, tl.k0, p.u_is_zero ? (int)p.n + 64 : z, bar);
-    sp_tma_load(p, FIELD_F, sm.F + so, tl.k0, z, bar);
-    sp_tma_load(p, FIELD_V1, sm.V1 + so, tl.k0, z, bar);
-    sp_tma_load(p, FIELD_V2, sm.V2 + so, tl.k0, z, bar);
-    if (p.pre) sp_tma_load(p, FIELD_C, sm.C + (long)gs * CROWS * 2 * p.CW, tl.k0 / 2, z >> 1, bar);
+    // tensor coordinates are memory rows; a zero iterate is produced by a box that lies entirely
+    // below the last memory row
+    const int zm = z - (int)p.row0;
+    sp_tma_load(p, FIELD_U, sm.U + so, tl.k0, p.u_is_zero ? (int)p.rows_mem + 64 : zm, bar);
+    sp_tma_load(p, FIELD_F, sm.F + so, tl.k0, zm, bar);
+    sp_tma_load(p, FIELD_V1, sm.V1 + so, tl.k0, zm, bar);
+    sp_tma_load(p, FIELD_V2, sm.V2 + so, tl.k0, zm, bar);
+    if (p.pre) sp_tma_load(p, FIELD_C, sm.C + (long)gs * CROWS * 2 * p.CW, tl.k0 / 2, (z >> 1) - (int)p.crow0, bar);
     // start the HBM fetch of the group after next: its shared-memory request will then hit L2
     const int zp = z + 2 * GROUP;
     if (zp <= tl.R1) {
-        if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp);
-        sp_tma_prefetch(p, FIELD_F, tl.k0, zp);
-        sp_tma_prefetch(p, FIELD_V1, tl.k0, zp);
-        sp_tma_prefetch(p, FIELD_V2, tl.k0, zp);
+        if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp - (int)p.row0);
+        sp_tma_prefetch(p, FIELD_F, tl.k0, zp - (int)p.row0);
+        sp_tma_prefetch(p, FIELD_V1, tl.k0, zp - (int)p.row0);
+        sp_tma_prefetch(p, FIELD_V2, tl.k0, zp - (int)p.row0);
     }
 }
 
@@ -199,7 +206,7 @@ SP_FN void issue_row_store(const Params& p, const Tile& tl, const Smem& sm, int 
     if (eO > p.nhalf) eO = p.nhalf;
     const long nE = (eE - tl.kb + 1) & ~1L;             // rounded up to a whole 16-byte unit (layout slack)
     const long nO = eO - tl.kb;
-    const long goff = (long)q * p.pitch + tl.kb;
+    const long goff = ((long)q - p.row0) * p.pitch + tl.kb;
     const long so = (long)slot * 2 * p.SWK + lo;
     if (nE > 0) sp_bulk_store(p.u_out + goff, sm.U + so, (unsigned)(nE * 8));
     if (nO > 0) sp_bulk_store(p.u_out + goff + p.odd, sm.U + so + p.SWK, (unsigned)(nO * 8));
@@ -238,6 +245,10 @@ struct ThreadState {
     int wgroup;         // its group slot
     unsigned wpar;      // and that barrier's phase parity
     double acc;         // POST_NORM2 accumulator
+    // stage: operands carried in registers from step to step (shared memory bandwidth is what
+    // bounds this kernel): the other-parity nodes of the current row become the next row's upper
+    // neighbours, the nodes loaded from the row below become the next row's horizontal neighbours
+    D2 c_up, c_mid;
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -259,7 +270,7 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 {
     ThreadState s;
     const int warp = tid >> 5, lane = tid & 31;
-    s.acc = 0.0; s.ok_cur = 0; s.okp[0] = s.okp[1] = 0; s.idx = 0; s.kk = 0; s.par = 0;
+    s.acc = 0.0; s.c_up = D2{0.0, 0.0}; s.c_mid = D2{0.0, 0.0}; s.ok_cur = 0; s.okp[0] = s.okp[1] = 0; s.idx = 0; s.kk = 0; s.par = 0;
     s.lo = 1; s.hi = 0;                                  // empty range
     int off = 0;                                         // role row = t - off
     if (warp < NSTAGE) {
@@ -308,12 +319,14 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 // nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd
 // columns: E[kk], E[kk+1], E[kk+2]).
 template <int ARITH, int PAR>
-SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, const ThreadState& st)
+SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
     const unsigned c = st.a_cur + po;
-    const D2 up = sp_lds2(sm, st.a_prev + po), dn = sp_lds2(sm, st.a_next + po);
-    const D2 m = sp_lds2(sm, st.a_cur + oo);
+    // up = run PAR of row-1 = what was `m` one step ago; m = run 1-PAR of row = what was `dn` one
+    // step ago (neither is written by any stage in between: see the lag argument at the top)
+    const D2 up = st.c_up, m = st.c_mid;
+    const D2 dn = sp_lds2(sm, st.a_next + po);
     const double x = sp_lds1(sm, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
     const D2 f = sp_lds2(sm, c + geo.ringb), w1 = sp_lds2(sm, c + 2u * geo.ringb), w2 = sp_lds2(sm, c + 3u * geo.ringb);
     const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
@@ -324,6 +337,7 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, const Thr
     const bool act = st.row >= st.lo && st.row <= st.hi;
     if (act && (st.okp[PAR] & 1u)) sp_sts1(sm, c, o0);
     if (act && (st.okp[PAR] & 2u)) sp_sts1(sm, c + 8u, o1);
+    st.c_up = m; st.c_mid = dn;
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
@@ -372,7 +386,7 @@ SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
                                                  sp_lds1(sm, st.a_next), uo, c, p.st);
         if (p.post == POST_INJECT) {
             const long kg = (long)tl.k0 + st.kk;
-            p.crhs[(long)(q >> 1) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;         // gs.cpp:283
+            p.crhs[((long)(q >> 1) - p.crow0) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;   // gs.cpp:283
         } else {
             st.acc += rv * rv;
         }
@@ -474,9 +488,10 @@ struct Plan { int WK, SWK, nstrips, nbands; long RBAND; };
 // resident tiles per SM: one (608 threads x ~90 registers fill the register file)
 inline int tiles_per_sm(int) { return 1; }
 
-inline Plan make_plan(long n, int K, int sms, int force_swk = 0)
+// n: level size (columns); nrows: rows this launch produces (n+1 on a single GPU, the slab otherwise)
+inline Plan make_plan(long n, long nrows, int K, int sms, int force_swk = 0)
 {
-    const long npairs = n / 2 + 1, nrows = n + 1;
+    const long npairs = n / 2 + 1;
     Plan best{};
     double best_cost = 1e300;
     for (int SWK = 32; SWK <= SWK_MAX; SWK += 16) {

@@ -38,7 +38,7 @@ SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, u
     const double* src = which == FIELD_U ? p.u_in : which == FIELD_F ? p.rhs : which == FIELD_V1 ? p.v1 : which == FIELD_V2 ? p.v2 : p.cu;
     const bool coarse = which == FIELD_C;
     const long odd = coarse ? p.codd : p.odd, pitch = coarse ? p.cpitch : p.pitch;
-    const long nrows = coarse ? p.nhalf + 1 : p.n + 1;
+    const long nrows = coarse ? p.crows_mem : p.rows_mem;
     const int inner = coarse ? p.CW : p.SWK, brows = coarse ? CROWS : GROUP;
     for (int zz = 0; zz < brows; ++zz)
         for (int par = 0; par < 2; ++par)
@@ -66,23 +66,28 @@ using namespace mgb200::sp;
 
 extern "C" {
 
-// Runs one pass over level n on HOST arrays in the split layout.  wk/nbands <= 0: use the planner.
+// Runs one pass over level n on HOST arrays in the split layout (rows_mem == 0: the whole level;
+// otherwise a row slab: the arrays hold global rows row0.. and rows own_lo..own_hi are produced).  wk/nbands <= 0: use the planner.
 // order: 0 ascending thread ids, 1 descending, 2 shuffled per step.  partials: >= ntiles doubles.
 // Returns the number of tiles, or -1 on a bad argument.
 long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const double* u_in, double* u_out,
                 const double* rhs, const double* v1, const double* v2, const double* cu, double* crhs,
                 double* partials, int K, int post, int arith, double dt, double nu, double dx, int wk, int nbands,
-                int order)
+                int order, long own_lo, long own_hi, long row0, long rows_mem, long crow0, long crows_mem)
 {
     if (K < 0 || K > KMAX || n < 8 || (n & 3)) return -1;
+    if (rows_mem == 0) { own_lo = 0; own_hi = n; row0 = 0; rows_mem = n + 1; crow0 = 0; crows_mem = n / 2 + 1; }
     Params p{};
     p.n = n; p.nhalf = n / 2; p.pitch = pitch; p.odd = odd; p.cpitch = cpitch; p.codd = codd;
-    Plan pl = make_plan(n, K, 148);
+    p.own_lo = own_lo; p.own_hi = own_hi; p.row0 = row0; p.rows_mem = rows_mem;
+    p.mem_lo = row0; p.mem_hi = row0 + rows_mem - 1; p.crow0 = crow0; p.crows_mem = crows_mem;
+    Plan pl = make_plan(n, own_hi - own_lo + 1, K, 148);
     if (wk > 0) {
         pl.WK = wk; pl.SWK = wk + 2 * HK; pl.nstrips = (int)((n / 2 + 1 + wk - 1) / wk);
     }
     if (nbands > 0) {
-        pl.RBAND = (n + 1 + nbands - 1) / nbands; pl.nbands = (int)((n + 1 + pl.RBAND - 1) / pl.RBAND);
+        const long nr = own_hi - own_lo + 1;
+        pl.RBAND = (nr + nbands - 1) / nbands; pl.nbands = (int)((nr + pl.RBAND - 1) / pl.RBAND);
     }
     if (pl.SWK > SWK_MAX || (pl.SWK & 15)) return -1;
     p.RBAND = pl.RBAND; p.WK = pl.WK; p.SWK = pl.SWK; p.nstrips = pl.nstrips; p.nbands = pl.nbands;

@@ -25,7 +25,7 @@ def emu():
                         "-I/usr/local/cuda/include", "-o", so, src[0]], check=True)
     lib = C.CDLL(so)
     lib.sp_emu_run.restype = C.c_long
-    lib.sp_emu_run.argtypes = [C.c_long] * 5 + [_dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 3
+    lib.sp_emu_run.argtypes = [C.c_long] * 5 + [_dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_long] * 6
     return lib
 
 
@@ -65,7 +65,7 @@ def run(emu, n, u, rhs, v1, v2, K, post, arith, dt, nu, dx, cu=None, wk=0, nband
     cus = None if cu is None else to_split(cu)
     nt = emu.sp_emu_run(n, pitch, odd, cp, co, ptr(us), ptr(out), ptr(to_split(rhs)), ptr(to_split(v1)),
                         ptr(to_split(v2)), ptr(cus), ptr(crhs), ptr(partials), K, post, arith, dt, nu, dx, wk, nbands,
-                        order)
+                        order, 0, 0, 0, 0, 0, 0)
     assert nt > 0
     return from_split(out, n), from_split(crhs, n // 2), partials[:nt]
 
