@@ -17,17 +17,28 @@ namespace sp {
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-SP_FN void sp_bar_expect(unsigned long long* bar, unsigned bytes)
+SP_FN bool sp_elect()
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    unsigned pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
-SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long* bar)
+SP_FN void sp_bar_expect(const Smem& sm, int bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm.base32 + sm.bar_off + 8u * bar), "r"(bytes) : "memory");
+}
+
+SP_FN void sp_tma_load(const Params& p, const Smem& sm, int which, unsigned soff, int x, int z, int bar)
 {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(sdst)),
-        "l"(&p.maps[which]), "r"(x), "r"(0), "r"(z), "r"(smem_u32(bar))
+            sm.base32 + soff),
+        "l"(&p.maps[which]), "r"(x), "r"(0), "r"(z), "r"(sm.base32 + sm.bar_off + 8u * bar)
         : "memory");
 }
 
@@ -37,9 +48,9 @@ SP_FN void sp_tma_prefetch(const Params& p, int which, int x, int z)
                  : "memory");
 }
 
-SP_FN void sp_bar_wait(unsigned long long* bar, unsigned parity)
+SP_FN void sp_bar_wait(const Smem& sm, int bar, unsigned parity)
 {
-    const unsigned a = smem_u32(bar);
+    const unsigned a = sm.base32 + sm.bar_off + 8u * bar;
     unsigned done;
     do {
         asm volatile(
@@ -52,9 +63,9 @@ SP_FN void sp_bar_wait(unsigned long long* bar, unsigned parity)
     } while (!done);
 }
 
-SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes)
+SP_FN void sp_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sm.base32 + soff), "r"(bytes) : "memory");
 }
 
 SP_FN void sp_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -150,7 +161,7 @@ __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const 
     } else if (st.role == ROLE_POST) {
         role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH>(p, tl, geo, sm, st); });
     } else {
-        role_loop(p, tl, geo, sm, st, [&](int t) { if (lane == 0) producer_step(p, tl, sm, t); });
+        role_loop(p, tl, geo, sm, st, [&](int t) { producer_step(p, tl, geo, sm, st, t); });
     }
 }
 
@@ -164,22 +175,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     sm.base32 = smem_u32(smem_raw);
     const Tile tl = make_tile(p, blockIdx.x);
     const Geo geo = make_geo(p);
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) {
+    // warp index through a shuffle: provably warp-uniform, so that role branches are uniform and
+    // the producer's operands live in uniform registers (no per-lane "waterfall" around TMA issue)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
         for (int s = 0; s < NGROUP; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.full[s])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm.base32 + sm.bar_off + 8u * s) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         sp_fence_async();
     }
     __syncthreads();
-    if (tid == PRODUCER_WARP * 32) producer_prologue(p, tl, sm);
-    ThreadState st = init_thread(p, tl, geo, tid);
+    if (warp == PRODUCER_WARP) producer_prologue(p, tl, geo, sm);
+    ThreadState st = init_thread(p, tl, geo, warp * 32 + lane);
     wait_first_row(sm);
     run_tile<ARITH>(p, tl, geo, sm, st, lane);
-    if (tid == PRODUCER_WARP * 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == PRODUCER_WARP && sp_elect()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
     if (p.post == POST_NORM2) {
         const double tot = block_sum(st.acc, scratch);
-        if (tid == 0) p.partials[blockIdx.x] = tot;
+        if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
     }
 }
 

@@ -96,15 +96,12 @@ struct Tile {
 };
 
 struct Smem {
-    unsigned char* raw;        // start of the dynamic shared memory (the U ring)
+    unsigned char* raw;        // start of the dynamic shared memory (generic address; host emulation)
     unsigned base32;           // its shared-space address (device only)
-    double* U;                 // [RING][2][SWK]
-    double* F;                 // rhs
-    double* V1;
-    double* V2;
-    double* C;                 // [NGROUP][CROWS][2][CW]
-    unsigned long long* full;  // [NGROUP] load-completion barriers
+    unsigned bar_off;          // byte offset of the NGROUP load-completion barriers
 };
+// byte offsets from `raw`: U ring at 0, rhs / v1 / v2 rings at ringb, 2 ringb, 3 ringb, the coarse
+// rows [NGROUP][CROWS][2][CW] at 4 ringb, then the barriers
 
 enum Field { FIELD_U = 0, FIELD_F = 1, FIELD_V1 = 2, FIELD_V2 = 3, FIELD_C = 4 };
 
@@ -120,12 +117,8 @@ struct alignas(16) D2 { double x, y; };    // 16-byte vector; aligned accesses o
 
 SP_FN void carve(Smem& sm, unsigned char* base, int swk)
 {
-    const size_t row = (size_t)RING * 2 * swk;
-    double* d = reinterpret_cast<double*>(base);
     sm.raw = base; sm.base32 = 0;
-    sm.U = d; sm.F = d + row; sm.V1 = d + 2 * row; sm.V2 = d + 3 * row;
-    sm.C = d + 4 * row;
-    sm.full = reinterpret_cast<unsigned long long*>(sm.C + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8));
+    sm.bar_off = (unsigned)(4 * RING * 2 * swk * 8 + NGROUP * CROWS * 2 * (swk / 2 + 8) * 8);
 }
 
 SP_FN Tile make_tile(const Params& p, long tile)
@@ -148,70 +141,26 @@ SP_FN int ring_slot(const Tile& tl, int row) { return (row - tl.R0) % RING; }
 
 
 // ------------------------------------------------------------------------------------------
-// asynchronous primitives
-SP_FN void sp_bar_expect(unsigned long long* bar, unsigned bytes);
+// primitives (inline PTX in stream_pass.cu, plain C++ in the host emulation).  Shared memory is
+// addressed by byte offsets from the start of the U ring, barriers by index.
+SP_FN bool sp_elect();                                   // true in exactly one lane of the converged warp
+SP_FN void sp_bar_expect(const Smem& sm, int bar, unsigned bytes);
 // 3-D tensor load of field `which`: box {SWK (CW for FIELD_C), 2, GROUP (CROWS)} whose first element
-// is (pair x, parity 0, row z) of the field; out-of-bounds elements arrive as zeros
-SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long* bar);
+// is (pair x, parity 0, memory row z) of the field; out-of-bounds elements arrive as zeros
+SP_FN void sp_tma_load(const Params& p, const Smem& sm, int which, unsigned soff, int x, int z, int bar);
 // same box, pulled into L2 only (no shared-memory destination)
 SP_FN void sp_tma_prefetch(const Params& p, int which, int x, int z);
-SP_FN void sp_bar_wait(unsigned long long* bar, unsigned parity);
-SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes);
+SP_FN void sp_bar_wait(const Smem& sm, int bar, unsigned parity);
+SP_FN void sp_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes);
 SP_FN void sp_store_commit();
 SP_FN void sp_store_wait_read2();
 SP_FN void sp_fence_async();
-// shared-memory accesses by byte offset from the start of the U ring (16-byte vectors need
-// 16-byte aligned offsets); on the device these are ld/st.shared with register+immediate addresses
+// 16-byte vectors need 16-byte aligned offsets; on the device these are ld/st.shared with
+// register+immediate addresses
 SP_FN D2 sp_lds2(const Smem& sm, unsigned off);
 SP_FN double sp_lds1(const Smem& sm, unsigned off);
 SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v);
 SP_FN void sp_sts1(const Smem& sm, unsigned off, double v);
-
-// ------------------------------------------------------------------------------------------
-// producer: request group g (rows R0+4g .. R0+4g+3) of the four fields, plus the three coarse rows
-// its prolongation needs; everything completes on full[g % NGROUP]
-SP_FN void issue_group_loads(const Params& p, const Tile& tl, const Smem& sm, int g)
-{
-    const int gs = g % NGROUP;
-    unsigned long long* bar = &sm.full[gs];
-    const int z = tl.R0 + GROUP * g;
-    const unsigned fine = (unsigned)(GROUP * 2 * p.SWK * 8), coarse = (unsigned)(CROWS * 2 * p.CW * 8);
-    sp_bar_expect(bar, 4u * fine + (p.pre ? coarse : 0u));
-    const long so = (long)gs * GROUP * 2 * p.SWK;
-    // tensor coordinates are memory rows; a zero iterate is produced by a box that lies entirely
-    // below the last memory row
-    const int zm = z - (int)p.row0;
-    sp_tma_load(p, FIELD_U, sm.U + so, tl.k0, p.u_is_zero ? (int)p.rows_mem + 64 : zm, bar);
-    sp_tma_load(p, FIELD_F, sm.F + so, tl.k0, zm, bar);
-    sp_tma_load(p, FIELD_V1, sm.V1 + so, tl.k0, zm, bar);
-    sp_tma_load(p, FIELD_V2, sm.V2 + so, tl.k0, zm, bar);
-    if (p.pre) sp_tma_load(p, FIELD_C, sm.C + (long)gs * CROWS * 2 * p.CW, tl.k0 / 2, (z >> 1) - (int)p.crow0, bar);
-    // start the HBM fetch of the group after next: its shared-memory request will then hit L2
-    const int zp = z + 2 * GROUP;
-    if (zp <= tl.R1) {
-        if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp - (int)p.row0);
-        sp_tma_prefetch(p, FIELD_F, tl.k0, zp - (int)p.row0);
-        sp_tma_prefetch(p, FIELD_V1, tl.k0, zp - (int)p.row0);
-        sp_tma_prefetch(p, FIELD_V2, tl.k0, zp - (int)p.row0);
-    }
-}
-
-// producer: bulk store of the owned part of finished row q
-SP_FN void issue_row_store(const Params& p, const Tile& tl, const Smem& sm, int q)
-{
-    const int slot = ring_slot(tl, q);
-    const int lo = tl.kb - tl.k0;                       // = HK
-    long eE = (long)tl.kb + p.WK, eO = eE;
-    if (eE > p.nhalf + 1) eE = p.nhalf + 1;
-    if (eO > p.nhalf) eO = p.nhalf;
-    const long nE = (eE - tl.kb + 1) & ~1L;             // rounded up to a whole 16-byte unit (layout slack)
-    const long nO = eO - tl.kb;
-    const long goff = ((long)q - p.row0) * p.pitch + tl.kb;
-    const long so = (long)slot * 2 * p.SWK + lo;
-    if (nE > 0) sp_bulk_store(p.u_out + goff, sm.U + so, (unsigned)(nE * 8));
-    if (nO > 0) sp_bulk_store(p.u_out + goff + p.odd, sm.U + so + p.SWK, (unsigned)(nO * 8));
-    sp_store_commit();
-}
 
 // ------------------------------------------------------------------------------------------
 // per-thread state, advanced by one row per step.  Rows are addressed by BYTE OFFSETS into the U
@@ -249,6 +198,12 @@ struct ThreadState {
     // bounds this kernel): the other-parity nodes of the current row become the next row's upper
     // neighbours, the nodes loaded from the row below become the next row's horizontal neighbours
     D2 c_up, c_mid;
+    // producer: next row to store and next group to request, all advanced incrementally
+    double* gst;        // global address of row `row`'s even run at the first owned pair
+    unsigned nE8, nO8;  // bytes of the owned parts of the even / odd run
+    int gnext;          // next group to request
+    int gz;             // its first row (memory row index)
+    int gslot;          // its group slot
 };
 
 // validity of a GS / residual target at local pair kk of parity par
@@ -292,7 +247,18 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
         }
         if (p.post != POST_NONE && s.ok_cur) { s.lo = tl.rb0 < 1 ? 1 : tl.rb0; s.hi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1; }
     } else {
-        s.role = ROLE_PRODUCER;
+        // the producer follows the row that is stored in the current step: finished one step earlier
+        s.role = ROLE_PRODUCER; s.kk = HK; off = 4 * p.K + 1;
+        if (p.write_u) { s.lo = tl.rb0; s.hi = tl.rb1; }
+    }
+    s.gst = nullptr; s.nE8 = s.nO8 = 0; s.gnext = 2; s.gz = tl.R0 + 2 * GROUP - (int)p.row0; s.gslot = 2 % NGROUP;
+    if (s.role == ROLE_PRODUCER) {
+        long eE = (long)tl.kb + p.WK, eO = eE;
+        if (eE > p.nhalf + 1) eE = p.nhalf + 1;
+        if (eO > p.nhalf) eO = p.nhalf;
+        s.nE8 = (unsigned)(((eE - tl.kb + 1) & ~1L) * 8);    // whole 16-byte units (the layout has slack)
+        s.nO8 = (unsigned)((eO - tl.kb) * 8);
+        s.gst = p.u_out + ((long)(tl.R0 - off) - p.row0) * p.pitch + tl.kb;
     }
     s.row = tl.R0 - off;
     const int slot = ((RING - off) % RING + RING) % RING;               // row R0 sits in slot 0
@@ -335,8 +301,14 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
     const double o0 = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
     const double o1 = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
     const bool act = st.row >= st.lo && st.row <= st.hi;
-    if (act && (st.okp[PAR] & 1u)) sp_sts1(sm, c, o0);
-    if (act && (st.okp[PAR] & 2u)) sp_sts1(sm, c + 8u, o1);
+    // one 16-byte store in the (warp-uniform but for strip edges) common case: two 8-byte stores
+    // at a 16-byte lane stride cost twice the shared-memory wavefronts
+    const unsigned okb = act ? st.okp[PAR] : 0u;
+    if (okb == 3u) sp_sts2(sm, c, D2{o0, o1});
+    else {
+        if (okb & 1u) sp_sts1(sm, c, o0);
+        if (okb & 2u) sp_sts1(sm, c + 8u, o1);
+    }
     st.c_up = m; st.c_mid = dn;
 }
 
@@ -404,28 +376,61 @@ SP_FN int first_step(const Tile& tl) { return tl.R0; }
 SP_FN int last_step(const Params& p, const Tile& tl) { return tl.rb1 + 4 * p.K + 2; }
 SP_FN int num_groups(const Tile& tl) { return (tl.R1 - tl.R0) / GROUP + 1; }
 
-// producer prologue: the first two groups
-SP_FN void producer_prologue(const Params& p, const Tile& tl, const Smem& sm)
+// producer: request the group starting at memory row z (global row z + row0) into group slot gs:
+// the four fields plus the three coarse rows its prolongation needs, all completing on barrier gs;
+// then start the HBM fetch of the group after next, whose shared-memory request will hit L2.
+// Executed by the whole (converged) producer warp with warp-uniform operands; one elected lane
+// issues the instructions.
+SP_FN void issue_group_loads(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, int z, int gs)
 {
-    const int ng = num_groups(tl);
-    for (int g = 0; g < 2 && g < ng; ++g) issue_group_loads(p, tl, sm, g);
+    if (!sp_elect()) return;
+    const unsigned fine = (unsigned)GROUP * geo.rowb, coarse = (unsigned)(CROWS * 2 * p.CW * 8);
+    sp_bar_expect(sm, gs, 4u * fine + (p.pre ? coarse : 0u));
+    const unsigned so = (unsigned)gs * fine;
+    // a zero iterate is produced by a box that lies entirely below the last memory row
+    sp_tma_load(p, sm, FIELD_U, so, tl.k0, p.u_is_zero ? (int)p.rows_mem + 64 : z, gs);
+    sp_tma_load(p, sm, FIELD_F, so + geo.ringb, tl.k0, z, gs);
+    sp_tma_load(p, sm, FIELD_V1, so + 2u * geo.ringb, tl.k0, z, gs);
+    sp_tma_load(p, sm, FIELD_V2, so + 3u * geo.ringb, tl.k0, z, gs);
+    if (p.pre)
+        sp_tma_load(p, sm, FIELD_C, 4u * geo.ringb + (unsigned)gs * coarse, tl.k0 / 2, ((z + (int)p.row0) >> 1) - (int)p.crow0, gs);
+    const int zp = z + 2 * GROUP;
+    if (zp + (int)p.row0 <= tl.R1) {
+        if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_F, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_V1, tl.k0, zp);
+        sp_tma_prefetch(p, FIELD_V2, tl.k0, zp);
+    }
 }
 
-SP_FN void producer_step(const Params& p, const Tile& tl, const Smem& sm, int t)
+// producer prologue (whole warp): the first two groups
+SP_FN void producer_prologue(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
 {
-    const int q = t - 4 * p.K - 1;                      // finished by the previous step
-    if (p.write_u && q >= tl.rb0 && q <= tl.rb1) issue_row_store(p, tl, sm, q);
-    // group g is requested LEAD steps before its first row: its ring slots were last read (row
-    // t-4K-3 and older) in the previous step
-    const int d = t + LEAD - tl.R0;
-    if (d % GROUP == 0 && d / GROUP >= 2 && d / GROUP < num_groups(tl)) {
-        sp_store_wait_read2();                          // the slots' previous rows have left shared memory
-        issue_group_loads(p, tl, sm, d / GROUP);
+    const int ng = num_groups(tl);
+    for (int g = 0; g < 2 && g < ng; ++g) issue_group_loads(p, tl, geo, sm, tl.R0 + GROUP * g - (int)p.row0, g);
+}
+
+// producer step t (whole warp): bulk-store the owned part of the row finished by the previous
+// step, and LEAD steps before a group's first row is consumed request it: its ring slots were last
+// read (row t-4K-3 and older) in the previous step.
+SP_FN void producer_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t)
+{
+    if (st.row >= st.lo && st.row <= st.hi && sp_elect()) {
+        if (st.nE8) sp_bulk_store(sm, st.gst, st.a_cur, st.nE8);
+        if (st.nO8) sp_bulk_store(sm, st.gst + p.odd, st.a_cur + geo.swkb, st.nO8);
+        sp_store_commit();
+    }
+    st.gst += p.pitch;
+    if (((t + LEAD - tl.R0) & (GROUP - 1)) == 0 && st.gnext < num_groups(tl)) {
+        if (sp_elect()) sp_store_wait_read2();          // the slots' previous rows have left shared memory
+        issue_group_loads(p, tl, geo, sm, st.gz, st.gslot);
+        st.gnext += 1; st.gz += GROUP;
+        st.gslot = st.gslot + 1 == NGROUP ? 0 : st.gslot + 1;
     }
 }
 
 // wait until the first group has landed (every thread, before the first step)
-SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(&sm.full[0], 0u); }
+SP_FN void wait_first_row(const Smem& sm) { sp_bar_wait(sm, 0, 0u); }
 
 // after a stage step: the next row has the other column parity
 SP_FN void stage_flip(ThreadState& st) { st.par ^= 1; }
@@ -445,8 +450,8 @@ SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
         if (p.K == 0) sp_fence_async();
     } else if (st.role == ROLE_POST) {
         post_step<ARITH>(p, tl, geo, sm, st);
-    } else if (lane == 0) {
-        producer_step(p, tl, sm, t);
+    } else {
+        producer_step(p, tl, geo, sm, st, t);
     }
 }
 
@@ -463,7 +468,7 @@ SP_FN void wait_group(const Tile& tl, const Smem& sm, ThreadState& st, int t)
 {
     st.wgroup += 1;
     if (st.wgroup == NGROUP) { st.wgroup = 0; st.wpar ^= 1u; }
-    if (t + 1 <= tl.R1) sp_bar_wait(&sm.full[st.wgroup], st.wpar);
+    if (t + 1 <= tl.R1) sp_bar_wait(sm, st.wgroup, st.wpar);
 }
 
 SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t)
@@ -474,7 +479,7 @@ SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState&
         st.wphase = 0;
         st.wgroup += 1;
         if (st.wgroup == NGROUP) { st.wgroup = 0; st.wpar ^= 1u; }
-        if (t + 1 <= tl.R1) sp_bar_wait(&sm.full[st.wgroup], st.wpar);
+        if (t + 1 <= tl.R1) sp_bar_wait(sm, st.wgroup, st.wpar);
     }
 }
 

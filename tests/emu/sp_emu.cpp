@@ -31,10 +31,13 @@ void set_error(const std::string&) {}
 int fail(int code, const std::string&) { return code; }
 long& launch_counter() { static long c = 0; return c; }
 namespace sp {
-SP_FN void sp_bar_expect(unsigned long long*, unsigned) {}
+static int g_lane = 0;   // lane of the thread being emulated
+SP_FN bool sp_elect() { return g_lane == 0; }
+SP_FN void sp_bar_expect(const Smem&, int, unsigned) {}
 // software model of the 3-D tensor copy: box {inner, 2, rows} at (x, 0, z), zeros outside the tensor
-SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, unsigned long long*)
+SP_FN void sp_tma_load(const Params& p, const Smem& sm, int which, unsigned soff, int x, int z, int)
 {
+    double* sdst = reinterpret_cast<double*>(sm.raw + soff);
     const double* src = which == FIELD_U ? p.u_in : which == FIELD_F ? p.rhs : which == FIELD_V1 ? p.v1 : which == FIELD_V2 ? p.v2 : p.cu;
     const bool coarse = which == FIELD_C;
     const long odd = coarse ? p.codd : p.odd, pitch = coarse ? p.cpitch : p.pitch;
@@ -49,8 +52,8 @@ SP_FN void sp_tma_load(const Params& p, int which, double* sdst, int x, int z, u
             }
 }
 SP_FN void sp_tma_prefetch(const Params&, int, int, int) {}
-SP_FN void sp_bar_wait(unsigned long long*, unsigned) {}
-SP_FN void sp_bulk_store(double* gdst, const double* ssrc, unsigned bytes) { std::memcpy(gdst, ssrc, bytes); }
+SP_FN void sp_bar_wait(const Smem&, int, unsigned) {}
+SP_FN void sp_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes) { std::memcpy(gdst, sm.raw + soff, bytes); }
 SP_FN void sp_store_commit() {}
 SP_FN void sp_store_wait_read2() {}
 SP_FN void sp_fence_async() {}
@@ -113,8 +116,8 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
         Smem sm;
         carve(sm, smem.data(), p.SWK);
         const Tile tl = make_tile(p, tile);
-        producer_prologue(p, tl, sm);
         const Geo geo = make_geo(p);
+        for (g_lane = 0; g_lane < 32; ++g_lane) producer_prologue(p, tl, geo, sm);
         std::vector<ThreadState> st(THREADS);
         for (int tid = 0; tid < THREADS; ++tid) st[tid] = init_thread(p, tl, geo, tid);
         wait_first_row(sm);
@@ -130,6 +133,7 @@ long sp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const doub
             for (int q = 0; q < THREADS; ++q) {
                 const int tid = perm[q];
                 const int lane = tid & 31;
+                g_lane = lane;
                 if (arith == MGB200_ARITH_EXACT) role_step<MGB200_ARITH_EXACT>(p, tl, geo, sm, st[tid], t, lane);
                 else role_step<MGB200_ARITH_FAST>(p, tl, geo, sm, st[tid], t, lane);
                 end_step(tl, geo, sm, st[tid], t);
