@@ -84,6 +84,14 @@ SP_FN double sp_lds1(const Smem& sm, unsigned off)
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sm.base32 + off));
     return v;
 }
+template <int DIR>
+SP_FN double sp_side_neighbour(const Smem& sm, const D2& mid, unsigned off)
+{
+    const int lane = threadIdx.x & 31;
+    double x = DIR < 0 ? __shfl_up_sync(0xffffffffu, mid.y, 1) : __shfl_down_sync(0xffffffffu, mid.x, 1);
+    if (lane == (DIR < 0 ? 0 : 31)) x = sp_lds1(sm, off);
+    return x;
+}
 SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v)
 {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(sm.base32 + off), "d"(v.x), "d"(v.y) : "memory");

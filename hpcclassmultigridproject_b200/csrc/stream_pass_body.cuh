@@ -161,6 +161,12 @@ SP_FN D2 sp_lds2(const Smem& sm, unsigned off);
 SP_FN double sp_lds1(const Smem& sm, unsigned off);
 SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v);
 SP_FN void sp_sts1(const Smem& sm, unsigned off, double v);
+// The stage warps' third horizontal neighbour: the node of the other run just left (DIR = -1:
+// mid.y of the previous lane) or just right (DIR = +1: mid.x of the next lane) of the lane's
+// vector `mid`; the warp's edge lane reads it from shared memory at `off`.  (The host emulation
+// always reads shared memory: the value is the same.)
+template <int DIR>
+SP_FN double sp_side_neighbour(const Smem& sm, const D2& mid, unsigned off);
 
 // ------------------------------------------------------------------------------------------
 // per-thread state, advanced by one row per step.  Rows are addressed by BYTE OFFSETS into the U
@@ -293,7 +299,7 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
     // step ago (neither is written by any stage in between: see the lag argument at the top)
     const D2 up = st.c_up, m = st.c_mid;
     const D2 dn = sp_lds2(sm, st.a_next + po);
-    const double x = sp_lds1(sm, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
+    const double x = sp_side_neighbour<PAR ? 1 : -1>(sm, m, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
     const D2 f = sp_lds2(sm, c + geo.ringb), w1 = sp_lds2(sm, c + 2u * geo.ringb), w2 = sp_lds2(sm, c + 3u * geo.ringb);
     const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
     const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);

@@ -59,6 +59,8 @@ SP_FN void sp_store_wait_read2() {}
 SP_FN void sp_fence_async() {}
 SP_FN D2 sp_lds2(const Smem& sm, unsigned off) { return *reinterpret_cast<const D2*>(sm.raw + off); }
 SP_FN double sp_lds1(const Smem& sm, unsigned off) { return *reinterpret_cast<const double*>(sm.raw + off); }
+template <int DIR>
+SP_FN double sp_side_neighbour(const Smem& sm, const D2&, unsigned off) { return sp_lds1(sm, off); }
 SP_FN void sp_sts2(const Smem& sm, unsigned off, D2 v) { *reinterpret_cast<D2*>(sm.raw + off) = v; }
 SP_FN void sp_sts1(const Smem& sm, unsigned off, double v) { *reinterpret_cast<double*>(sm.raw + off) = v; }
 }  // namespace sp
