@@ -167,7 +167,8 @@ __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const 
     } else if (st.role == ROLE_PRE) {
         role_loop(p, tl, geo, sm, st, [&](int) { pre_step(p, tl, geo, sm, st); if (p.K == 0) sp_fence_async(); });
     } else if (st.role == ROLE_POST) {
-        role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH>(p, tl, geo, sm, st); });
+        if (st.par) role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 1>(p, tl, geo, sm, st); });
+        else role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 0>(p, tl, geo, sm, st); });
     } else {
         role_loop(p, tl, geo, sm, st, [&](int t) { producer_step(p, tl, geo, sm, st, t); });
     }

@@ -14,8 +14,8 @@
 // Redundant work: HK halo pairs per strip side, 2K+1 halo rows per band side (recomputed, never
 // stored); tiles write to u_out != u_in, so no tile ever sees another tile's results.
 //
-// Warp roles (19 warps): 12 stage warps (two per half-sweep, 2 nodes per lane as one 16-byte
-// vector), 2 prolongation warps, 4 residual-epilogue warps, 1 producer warp (one lane drives the
+// Warp roles (23 warps): 12 stage warps (two per half-sweep, 2 nodes per lane as one 16-byte
+// vector), 2 prolongation warps, 8 residual-epilogue warps (one node per lane), 1 producer warp (one lane drives the
 // TMA engine).  A warp's step is an almost serial dependency chain (address -> LDS -> 6 dependent
 // FP64 operations -> STS), so the block is wide (many short chains) rather than deep.  Per-thread state that advances by one row per step (ring slots, rows) is kept
 // incrementally, so a step has no division and almost no address arithmetic.
@@ -50,7 +50,7 @@ constexpr int KMAX = 3;
 constexpr int NSTW = 2;        // warps per half-sweep stage (64 pairs each)
 constexpr int NSTAGE = 2 * KMAX * NSTW;
 constexpr int NPRE = 2;        // prolongation warps (64 pairs each)
-constexpr int NPOST = 4;       // residual-epilogue warps (32 pairs each)
+constexpr int NPOST = 8;       // residual-epilogue warps: 4 x 32 even-column nodes, 4 x 32 odd-column nodes
 constexpr int WARPS = NSTAGE + NPRE + NPOST + 1;
 constexpr int THREADS = WARPS * 32;
 constexpr int PRODUCER_WARP = WARPS - 1;
@@ -246,11 +246,10 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
         }
         if (p.pre && (s.ok_cur & 3u)) { s.lo = tl.R0 < 1 ? 1 : tl.R0; s.hi = tl.R1 > p.n - 1 ? (int)p.n - 1 : tl.R1; }
     } else if (warp < NSTAGE + NPRE + NPOST) {
-        s.role = ROLE_POST; s.idx = warp - NSTAGE - NPRE; s.kk = HK + 32 * s.idx + lane; off = 4 * p.K + 2;
-        if (s.kk < HK + p.WK) {                          // owned pairs only
-            if (target_ok(p, tl, s.kk, 0)) s.ok_cur |= 1u;
-            if (p.post == POST_NORM2 && target_ok(p, tl, s.kk, 1)) s.ok_cur |= 2u;
-        }
+        // warps 0-3: the even-column node of pair kk, warps 4-7: the odd-column node (norm only)
+        s.role = ROLE_POST; s.idx = warp - NSTAGE - NPRE; s.kk = HK + 32 * (s.idx & 3) + lane; off = 4 * p.K + 2;
+        s.par = s.idx >> 2;
+        if (s.kk < HK + p.WK && (s.par == 0 || p.post == POST_NORM2) && target_ok(p, tl, s.kk, s.par)) s.ok_cur = 1u;   // owned nodes only
         if (p.post != POST_NONE && s.ok_cur) { s.lo = tl.rb0 < 1 ? 1 : tl.rb0; s.hi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1; }
     } else {
         // the producer follows the row that is stored in the current step: finished one step earlier
@@ -349,30 +348,26 @@ SP_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem&
     if (st.ok_cur & 2u) sp_sts1(sm, st.a_cur + geo.swkb + 8u, __dadd_rn(uo.y, o1));
 }
 
-// residual epilogue on finished row q: injection into the coarse rhs or sum of squares
-template <int ARITH>
+// residual epilogue on finished row q, one node per lane (PAR = its column parity): injection into
+// the coarse rhs (even columns of even rows) or sum of squares
+template <int ARITH, int PAR>
 SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const int q = st.row;
     if (q < st.lo || q > st.hi) return;
     if (p.post == POST_INJECT && (q & 1)) return;
-    const unsigned e = st.a_cur, o = st.a_cur + geo.swkb;
-    const double ue = sp_lds1(sm, e), uo = sp_lds1(sm, o);
-    if (st.ok_cur & 1u) {                                // even column 2kg
-        const Coef4 c = Arith<ARITH>::coef(sp_lds1(sm, e + 2u * geo.ringb), sp_lds1(sm, e + 3u * geo.ringb), p.st);
-        const double rv = Arith<ARITH>::residual(sp_lds1(sm, e + geo.ringb), ue, sp_lds1(sm, st.a_prev), sp_lds1(sm, o - 8u),
-                                                 sp_lds1(sm, st.a_next), uo, c, p.st);
-        if (p.post == POST_INJECT) {
-            const long kg = (long)tl.k0 + st.kk;
-            p.crhs[((long)(q >> 1) - p.crow0) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;   // gs.cpp:283
-        } else {
-            st.acc += rv * rv;
-        }
-    }
-    if (st.ok_cur & 2u) {                                // odd column 2kg+1 (POST_NORM2 only)
-        const Coef4 c = Arith<ARITH>::coef(sp_lds1(sm, o + 2u * geo.ringb), sp_lds1(sm, o + 3u * geo.ringb), p.st);
-        const double rv = Arith<ARITH>::residual(sp_lds1(sm, o + geo.ringb), uo, sp_lds1(sm, st.a_prev + geo.swkb), ue,
-                                                 sp_lds1(sm, st.a_next + geo.swkb), sp_lds1(sm, e + 8u), c, p.st);
+    const unsigned po = PAR ? geo.swkb : 0u;
+    const unsigned c = st.a_cur + po;                     // the node itself
+    const unsigned o = st.a_cur + (geo.swkb - po);        // the other run at the same pair index
+    const double u = sp_lds1(sm, c), up = sp_lds1(sm, st.a_prev + po), dn = sp_lds1(sm, st.a_next + po);
+    // even column: left = O[kk-1], right = O[kk]; odd column: left = E[kk], right = E[kk+1]
+    const double lf = sp_lds1(sm, PAR ? o : o - 8u), rt = sp_lds1(sm, PAR ? o + 8u : o);
+    const Coef4 k = Arith<ARITH>::coef(sp_lds1(sm, c + 2u * geo.ringb), sp_lds1(sm, c + 3u * geo.ringb), p.st);
+    const double rv = Arith<ARITH>::residual(sp_lds1(sm, c + geo.ringb), u, up, lf, dn, rt, k, p.st);
+    if (p.post == POST_INJECT) {
+        const long kg = (long)tl.k0 + st.kk;
+        p.crhs[((long)(q >> 1) - p.crow0) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;       // gs.cpp:283
+    } else {
         st.acc += rv * rv;
     }
 }
@@ -455,7 +450,8 @@ SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
         pre_step(p, tl, geo, sm, st);
         if (p.K == 0) sp_fence_async();
     } else if (st.role == ROLE_POST) {
-        post_step<ARITH>(p, tl, geo, sm, st);
+        if (st.par) post_step<ARITH, 1>(p, tl, geo, sm, st);
+        else post_step<ARITH, 0>(p, tl, geo, sm, st);
     } else {
         producer_step(p, tl, geo, sm, st, t);
     }
