@@ -186,7 +186,12 @@ def run_own(args, rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
-    s = mg.Solver(n, NU, dt, dx, TOL, plan=plan, arith=arith, device=local)
+    uid = None
+    if world > 1:
+        box = [mg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    s = mg.Solver(n, NU, dt, dx, TOL, plan=plan, arith=arith, device=local, rank=rank, nranks=world, unique_id=uid)
     s.set_fields_reference_ic(VSCALE)
     s.synchronize()
     for _ in range(args.warmup):
@@ -224,11 +229,13 @@ def run_own(args, rank, world):
         except Exception:
             traffic = None
     cycle_bytes = s.cycle_bytes
-    s.close()
+    slab = s.slab(0)
+    if world == 1:
+        s.close()
 
     # ---- e2e through the reference-facing entry point, host buffers, copies timed ----------
     e2e = None
-    if rank == 0 and not args.no_e2e:
+    if not args.no_e2e and world == 1:
         d = [torch.empty(n + 1, n + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
         mg.ops.initial_conditions(*d, n, VSCALE)
         host = [torch.empty(n + 1, n + 1, dtype=torch.float64).pin_memory() for _ in range(4)]
@@ -248,8 +255,42 @@ def run_own(args, rank, world):
                "d2h_bytes_per_step": int(m0 * 8), "call": "mgb200_timestepper_host (timestepper, multigrid.cpp:124), T=dt",
                "ms_per_call": 1e3 * sum(tt) / len(tt), "cycles_per_call": cyc / len(tt)}
         del host
-    if world > 1 and e2e is None and rank == 0:
-        e2e = None
+    elif not args.no_e2e:
+        # sharded: the same sequence through the handle API, every rank moving its own row slab:
+        # pinned host slab (+halo, + the rows the coarse-velocity towers read) -> device, one time
+        # step, owned rows of the result -> pinned host
+        import numpy as np
+        rows = slice(slab["mem_lo"], slab["mem_hi"] + 1)
+        d = [torch.empty(n + 1, n + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
+        mg.ops.initial_conditions(*d, n, VSCALE)
+        host = [torch.empty(n + 1, n + 1, dtype=torch.float64).pin_memory() for _ in range(4)]
+        for h, t in zip(host, d):
+            h.copy_(t)
+        del d
+        torch.cuda.synchronize(); torch.cuda.empty_cache()
+        reps, tt, cyc = max(1, min(args.steps, 3)), [], 0
+        for k in range(1 + reps):
+            barrier()
+            t0 = time.perf_counter()
+            s.set_fields_host(host[0], host[1], host[2])
+            info = s.timestep(1)[0]
+            s.get_u_host(host[3])
+            barrier()
+            el = time.perf_counter() - t0
+            if k >= 1:
+                tt.append(el); cyc += info.cycles
+        t = torch.tensor([sum(tt)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        own_rows = slab["own_hi"] - slab["own_lo"] + 1
+        win_rows = slab["mem_hi"] - slab["mem_lo"] + 1 + 2 * (n // 4 + 2) // 3 * 0
+        e2e = {"value": 1e3 * float(t.item()) / max(1, cyc), "unit": "ms",
+               "h2d_bytes_per_step": int(world * (3 * win_rows + 2 * (n // 4 + 2)) * (n + 1) * 8),
+               "d2h_bytes_per_step": int(m0 * 8),
+               "call": "mgb200_set_fields_host + mgb200_timestep(1) + mgb200_get_u_host on every rank's slab",
+               "ms_per_call": 1e3 * float(t.item()) / len(tt), "cycles_per_call": cyc / len(tt)}
+        del host
+    if world > 1:
+        s.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -60,6 +60,10 @@ def lib():
     L.mgb200_default_options.argtypes = [C.POINTER(Options)]
     L.mgb200_default_options.restype = None
     L.mgb200_create.argtypes = [C.POINTER(_vp), _l, _i, _d, _d, _d, _d, C.POINTER(Options)]
+    L.mgb200_comm_unique_id.argtypes = [C.c_char_p]
+    L.mgb200_create_sharded.argtypes = [C.POINTER(_vp), _l, _i, _d, _d, _d, _d, C.POINTER(Options), _i, _i, C.c_char_p, _l]
+    L.mgb200_slab.argtypes = [_vp, _i, C.POINTER(_l * 6)]
+    L.mgb200_slab_plan.argtypes = [_l, _i, _i, _i, _l, _i, C.POINTER(_l * 6)]
     L.mgb200_destroy.argtypes = [_vp]
     L.mgb200_set_fields_device.argtypes = [_vp, _vp, _vp, _vp, _l]
     L.mgb200_set_fields_host.argtypes = [_vp, _vp, _vp, _vp]
@@ -112,6 +116,21 @@ def default_options(**kw) -> Options:
     for k, v in kw.items():
         setattr(o, k, v)
     return o
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 creates it, the host program broadcasts it)"""
+    buf = C.create_string_buffer(128)
+    _ck(lib().mgb200_comm_unique_id(buf))
+    return buf.raw
+
+
+def slab_plan(n, maxlvl, nranks, rank, lvl, shard_min_rows=0):
+    """row window of `rank` at level `lvl` (pure arithmetic, needs no GPU):
+    dict(sharded, present, own_lo, own_hi, mem_lo, mem_hi)"""
+    out = (_l * 6)()
+    _ck(lib().mgb200_slab_plan(n, maxlvl, nranks, rank, shard_min_rows, lvl, C.byref(out)))
+    return dict(zip(("sharded", "present", "own_lo", "own_hi", "mem_lo", "mem_hi"), [int(x) for x in out]))
 
 
 class _Ops:
@@ -169,12 +188,24 @@ ops = _Ops()
 class Solver:
     """mgb200_solver handle: the V/W-cycle driver (mg_inner / mg_outer / timestepper)."""
 
-    def __init__(self, n, nu, dt, dx, tol, maxlvl=None, **opts):
+    def __init__(self, n, nu, dt, dx, tol, maxlvl=None, rank=0, nranks=1, unique_id=None, shard_min_rows=0, **opts):
+        """nranks > 1: row-slab sharded handle (one process per GPU); unique_id = comm_unique_id() of rank 0"""
         self.n = n
         self.maxlvl = maxlvl_for(n) if maxlvl is None else maxlvl
         self.opt = default_options(**opts)
+        self.rank, self.nranks = rank, nranks
         self.h = _vp()
-        _ck(lib().mgb200_create(C.byref(self.h), n, self.maxlvl, nu, dt, dx, tol, C.byref(self.opt)))
+        if nranks == 1:
+            _ck(lib().mgb200_create(C.byref(self.h), n, self.maxlvl, nu, dt, dx, tol, C.byref(self.opt)))
+        else:
+            assert unique_id is not None and len(unique_id) == 128
+            _ck(lib().mgb200_create_sharded(C.byref(self.h), n, self.maxlvl, nu, dt, dx, tol, C.byref(self.opt), rank, nranks,
+                                            unique_id, shard_min_rows))
+
+    def slab(self, lvl=0):
+        out = (_l * 6)()
+        _ck(lib().mgb200_slab(self.h, lvl, C.byref(out)))
+        return dict(zip(("sharded", "present", "own_lo", "own_hi", "mem_lo", "mem_hi"), [int(x) for x in out]))
 
     def close(self):
         if getattr(self, "h", None):
@@ -234,7 +265,7 @@ class Solver:
     def get_u_host(self, out=None):
         import numpy as np
         if out is None:
-            out = np.empty((self.n + 1, self.n + 1))
+            out = np.full((self.n + 1, self.n + 1), np.nan) if self.nranks > 1 else np.empty((self.n + 1, self.n + 1))
         _ck(lib().mgb200_get_u_host(self.h, _ptr(out)))
         return out
 
@@ -243,9 +274,10 @@ class Solver:
         return out
 
     def level(self, lvl, which="u"):
+        """dense copy of a level array; a slab rank fills only the rows it holds (the rest is NaN)"""
         import numpy as np
         nl = self.n >> lvl
-        out = np.empty((nl + 1, nl + 1))
+        out = np.full((nl + 1, nl + 1), np.nan)
         _ck(lib().mgb200_get_level_host(self.h, lvl, {"u": 0, "rhs": 1, "v1": 2, "v2": 3}[which], _ptr(out)))
         return out
 

@@ -57,21 +57,22 @@ static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 // doubles (128 B).
 struct Layout {
     long pitch;
-    long odd;   // < 0 : natural layout
+    long odd;        // < 0 : natural layout
+    long row0 = 0;   // global index of the first row held by the array (row slabs; 0 = whole field)
     __host__ __device__ __forceinline__ long at(long i, long j) const
     {
-        return odd < 0 ? i * pitch + j : i * pitch + (j & 1) * odd + (j >> 1);
+        return odd < 0 ? (i - row0) * pitch + j : (i - row0) * pitch + (j & 1) * odd + (j >> 1);
     }
     __host__ __device__ __forceinline__ bool split() const { return odd >= 0; }
 };
 
-static inline Layout natural_layout(long ld) { return Layout{ld, -1}; }
+static inline Layout natural_layout(long ld, long row0 = 0) { return Layout{ld, -1, row0}; }
 // n even.  Even run: n/2+1 nodes, odd run: n/2 nodes; 32 doubles of slack after each run so that
 // aligned, slightly over-long bulk copies of the streaming kernels stay inside the row.
 static inline Layout split_layout(long n)
 {
     long odd = round_up(n / 2 + 1, 16) + 32;
-    return Layout{2 * odd, odd};
+    return Layout{2 * odd, odd, 0};
 }
 static inline size_t layout_elems(const Layout& L, long n) { return (size_t)L.pitch * (size_t)(n + 1); }
 

@@ -70,15 +70,16 @@ __global__ void __launch_bounds__(TPB) k_residual(double* __restrict__ res, cons
 template <int ARITH, bool WITH_RES0>
 __global__ void __launch_bounds__(TPB) k_compute_rhs(double* __restrict__ rhs, const double* __restrict__ u,
                                                      const double* __restrict__ v1, const double* __restrict__ v2,
-                                                     long n, Layout L, Stencil st, double* __restrict__ partials)
+                                                     long n, Layout L, Stencil st, double* __restrict__ partials,
+                                                     long ilo, long ihi)
 {
     __shared__ double scratch[32];
     const long j = 1 + (long)blockIdx.y * TPB + threadIdx.x;
-    const long i0 = 1 + (long)blockIdx.x * ROWS_PER_BLOCK;
+    const long i0 = ilo + (long)blockIdx.x * ROWS_PER_BLOCK;
     double acc = 0.0;
     for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
         const long i = i0 + r;
-        if (i >= n || j >= n) break;
+        if (i > ihi || j >= n) break;
         const long q = L.at(i, j);
         const Coef4 c = Arith<ARITH>::coef(v1[q], v2[q], st);
         const double uc = u[q], up = u[L.at(i - 1, j)], lf = u[L.at(i, j - 1)], dn = u[L.at(i + 1, j)],
@@ -181,29 +182,30 @@ __global__ void __launch_bounds__(TPB) k_vecadd(double* __restrict__ c, const do
 }
 
 __global__ void __launch_bounds__(TPB) k_convert(double* __restrict__ dst, Layout Ld, const double* __restrict__ src,
-                                                 Layout Ls, long n)
+                                                 Layout Ls, long n, long ilo, long ihi)
 {
     const long j = (long)blockIdx.y * TPB + threadIdx.x;
-    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    const long i0 = ilo + (long)blockIdx.x * ROWS_PER_BLOCK;
     for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
         const long i = i0 + r;
-        if (i > n || j > n) break;
+        if (i > ihi || j > n) break;
         dst[Ld.at(i, j)] = src[Ls.at(i, j)];
     }
 }
 
 __global__ void __launch_bounds__(TPB) k_initial_conditions(double* __restrict__ u0, double* __restrict__ v1,
-                                                            double* __restrict__ v2, long n, Layout L, double vscale)
+                                                            double* __restrict__ v2, long n, Layout L, double vscale,
+                                                            long ilo, long ihi)
 {
     const double PI = 3.1415926535897932;                    // multigrid.cpp:14
     const double x0 = 0.2, y0 = 0.4, sigma = 100.0;          // multigrid.cpp:206-207
     const double kx = 1.0 * PI, ky = 1.0 * PI;
     const double dx = 1.0 / (double)n;
     const long j = (long)blockIdx.y * TPB + threadIdx.x;
-    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    const long i0 = ilo + (long)blockIdx.x * ROWS_PER_BLOCK;
     for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
         const long i = i0 + r;
-        if (i > n || j > n) break;
+        if (i > ihi || j > n) break;
         const double x = i * dx, y = j * dx;
         double g = exp(-sigma * ((x - x0) * (x - x0) + (y - y0) * (y - y0)));        // multigrid.cpp:219
         // boundary lines zeroed with a loop bound of N: node (N,0) keeps its value (multigrid.cpp:227-233)
@@ -234,13 +236,13 @@ __global__ void __launch_bounds__(TPB) k_tower_flat(double* __restrict__ flat_ou
 }
 
 __global__ void __launch_bounds__(TPB) k_flat_to_level(double* __restrict__ dst, Layout Ld,
-                                                       const double* __restrict__ flat, long nl)
+                                                       const double* __restrict__ flat, long nl, long ilo, long ihi)
 {
     const long j = (long)blockIdx.y * TPB + threadIdx.x;
-    const long i0 = (long)blockIdx.x * ROWS_PER_BLOCK;
+    const long i0 = ilo + (long)blockIdx.x * ROWS_PER_BLOCK;
     for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
         const long i = i0 + r;
-        if (i > nl || j > nl) break;
+        if (i > ihi || j > nl) break;
         dst[Ld.at(i, j)] = flat[i * (nl + 1) + j];
     }
 }
@@ -331,6 +333,12 @@ long residual_partials_count(long n)
     return (long)g.x * g.y;
 }
 
+long rows_partials_count(long n, long nrows)
+{
+    dim3 g = tile_grid(nrows, n - 1);
+    return (long)g.x * g.y;
+}
+
 int launch_gs_colour(double* u, const double* rhs, const double* v1, const double* v2, long n, Layout L,
                      const Stencil& st, int colour, int arith, cudaStream_t s)
 {
@@ -361,16 +369,18 @@ int launch_residual(double* res, const double* u, const double* rhs, const doubl
 }
 
 int launch_compute_rhs(double* rhs, const double* u, const double* v1, const double* v2, long n, Layout L,
-                       const Stencil& st, int arith, double* partials, cudaStream_t s)
+                       const Stencil& st, int arith, double* partials, cudaStream_t s, long row_lo, long row_hi)
 {
     if (n < 2) return MGB200_OK;
-    dim3 g = tile_grid(n - 1, n - 1);
+    const long ilo = row_lo < 1 ? 1 : row_lo, ihi = (row_hi < 0 || row_hi > n - 1) ? n - 1 : row_hi;
+    if (ihi < ilo) return MGB200_OK;
+    dim3 g = tile_grid(ihi - ilo + 1, n - 1);
     if (arith == MGB200_ARITH_EXACT) {
-        if (partials) k_compute_rhs<MGB200_ARITH_EXACT, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
-        else k_compute_rhs<MGB200_ARITH_EXACT, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+        if (partials) k_compute_rhs<MGB200_ARITH_EXACT, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+        else k_compute_rhs<MGB200_ARITH_EXACT, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
     } else {
-        if (partials) k_compute_rhs<MGB200_ARITH_FAST, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
-        else k_compute_rhs<MGB200_ARITH_FAST, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials);
+        if (partials) k_compute_rhs<MGB200_ARITH_FAST, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+        else k_compute_rhs<MGB200_ARITH_FAST, false><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
     }
     return check_launch("k_compute_rhs");
 }
@@ -417,15 +427,20 @@ int launch_vecadd(double* c, const double* a, const double* b, long n, Layout L,
     return check_launch("k_vecadd");
 }
 
-int launch_convert(double* dst, Layout Ld, const double* src, Layout Ls, long n, cudaStream_t s)
+int launch_convert(double* dst, Layout Ld, const double* src, Layout Ls, long n, cudaStream_t s, long row_lo, long row_hi)
 {
-    k_convert<<<tile_grid(n + 1, n + 1), TPB, 0, s>>>(dst, Ld, src, Ls, n);
+    const long ilo = row_lo < 0 ? 0 : row_lo, ihi = (row_hi < 0 || row_hi > n) ? n : row_hi;
+    if (ihi < ilo) return MGB200_OK;
+    k_convert<<<tile_grid(ihi - ilo + 1, n + 1), TPB, 0, s>>>(dst, Ld, src, Ls, n, ilo, ihi);
     return check_launch("k_convert");
 }
 
-int launch_initial_conditions(double* u0, double* v1, double* v2, long n, Layout L, double vscale, cudaStream_t s)
+int launch_initial_conditions(double* u0, double* v1, double* v2, long n, Layout L, double vscale, cudaStream_t s,
+                              long row_lo, long row_hi)
 {
-    k_initial_conditions<<<tile_grid(n + 1, n + 1), TPB, 0, s>>>(u0, v1, v2, n, L, vscale);
+    const long ilo = row_lo < 0 ? 0 : row_lo, ihi = (row_hi < 0 || row_hi > n) ? n : row_hi;
+    if (ihi < ilo) return MGB200_OK;
+    k_initial_conditions<<<tile_grid(ihi - ilo + 1, n + 1), TPB, 0, s>>>(u0, v1, v2, n, L, vscale, ilo, ihi);
     return check_launch("k_initial_conditions");
 }
 
@@ -436,9 +451,11 @@ int launch_tower_flat(double* flat_out, const double* src, bool from_level0, Lay
     return check_launch("k_tower_flat");
 }
 
-int launch_flat_to_level(double* dst, Layout Ld, const double* flat, long nl, cudaStream_t s)
+int launch_flat_to_level(double* dst, Layout Ld, const double* flat, long nl, cudaStream_t s, long row_lo, long row_hi)
 {
-    k_flat_to_level<<<tile_grid(nl + 1, nl + 1), TPB, 0, s>>>(dst, Ld, flat, nl);
+    const long ilo = row_lo < 0 ? 0 : row_lo, ihi = (row_hi < 0 || row_hi > nl) ? nl : row_hi;
+    if (ihi < ilo) return MGB200_OK;
+    k_flat_to_level<<<tile_grid(ihi - ilo + 1, nl + 1), TPB, 0, s>>>(dst, Ld, flat, nl, ilo, ihi);
     return check_launch("k_flat_to_level");
 }
 

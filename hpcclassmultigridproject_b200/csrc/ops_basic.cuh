@@ -19,8 +19,11 @@ int launch_residual(double* res, const double* u, const double* rhs, const doubl
                     long n, Layout L, const Stencil& st, int arith, double* partials, cudaStream_t s);
 long residual_partials_count(long n);
 // rhs = B u (interior); if partials != null also the squares of (rhs - A u)  -- gs.cpp:24-53
+// row_lo/row_hi (optional) restrict the rows produced (row slabs); partials then has
+// rows_partials_count(n, rows) entries
 int launch_compute_rhs(double* rhs, const double* u, const double* v1, const double* v2, long n, Layout L,
-                       const Stencil& st, int arith, double* partials, cudaStream_t s);
+                       const Stencil& st, int arith, double* partials, cudaStream_t s, long row_lo = 1, long row_hi = -1);
+long rows_partials_count(long n, long nrows);
 // sum of squares over the interior of a -> partials (same count as residual_partials_count)
 int launch_square_partials(const double* a, long n, Layout L, double* partials, cudaStream_t s);
 // out[0] = sum(partials[0..count)) in a fixed order (single block)
@@ -33,16 +36,17 @@ int launch_restrict_interior(double* coarse, Layout Lc, const double* fine, Layo
 int launch_prolong(double* fine, Layout Lf, const double* coarse, Layout Lc, long nc, bool add, cudaStream_t s);
 int launch_vecadd(double* c, const double* a, const double* b, long n, Layout L, cudaStream_t s);
 // dst(layout Ld) = src(layout Ls) over the (n+1)^2 nodes
-int launch_convert(double* dst, Layout Ld, const double* src, Layout Ls, long n, cudaStream_t s);
+int launch_convert(double* dst, Layout Ld, const double* src, Layout Ls, long n, cudaStream_t s, long row_lo = 0, long row_hi = -1);
 // reference ICs (multigrid.cpp:206-233), velocity times vscale
-int launch_initial_conditions(double* u0, double* v1, double* v2, long n, Layout L, double vscale, cudaStream_t s);
+int launch_initial_conditions(double* u0, double* v1, double* v2, long n, Layout L, double vscale, cudaStream_t s,
+                              long row_lo = 0, long row_hi = -1);
 // coarse velocity towers, reference-compatible (multigrid.cpp:148-160):
 //   flat_out[i*(q+1)+j] = src_flat[2i*(h+1)+2j], i,j in [0,q], q = N/4, h = N/2,
 // where src_flat is either the dense level-0 field read through (layout, N) [from_level0] or a
 // previous flat buffer.  flat buffers hold (h+1)^2 doubles and must be zero-filled beforehand.
 int launch_tower_flat(double* flat_out, const double* src, bool from_level0, Layout L0, long N, cudaStream_t s);
 // level array (split layout, n_l) = flat[i*(n_l+1)+j]
-int launch_flat_to_level(double* dst, Layout Ld, const double* flat, long nl, cudaStream_t s);
+int launch_flat_to_level(double* dst, Layout Ld, const double* flat, long nl, cudaStream_t s, long row_lo = 0, long row_hi = -1);
 // coarsest level solved on the device by ONE thread block: u = 0 (if zero_init); repeat
 // { RB-GS ; residual ; norm } until norm <= tol or maxit  (multigrid.cpp:55-65).  n <= 64.
 // iters_out (device int, may be null) receives the iteration count.

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <vector>
 
+#include "comm.cuh"
 #include "ops_basic.cuh"
 #include "stream_pass.cuh"
 
@@ -55,13 +56,50 @@ Stencil make_stencil(double dt, double nu, double dx)
 
 struct Level {
     long n = 0;
-    Layout L{0, 0};
+    Layout L{0, 0};                    // split layout; L.row0 = first row held (row slabs)
     Stencil st{};
     size_t elems = 0;
     double* u[2] = {nullptr, nullptr};
     int cur = 0;                       // which of u[] holds the current iterate
     double *rhs = nullptr, *v1 = nullptr, *v2 = nullptr;
+    // row window.  A single GPU owns and holds rows 0..n of every level.  With P ranks the fine
+    // levels are cut into row slabs (own rows + HALO rows received from the slab neighbours); the
+    // coarse levels live whole on rank 0, and the first of them also as a slab on the other ranks
+    // (target of the injection, source of the prolongation).
+    long own_lo = 0, own_hi = 0;       // rows this rank produces
+    long mem_lo = 0, mem_hi = 0;       // rows held in memory
+    bool sharded = false;              // cut across all ranks
+    bool present = true;               // arrays exist on this rank
+    long rows_mem() const { return mem_hi - mem_lo + 1; }
 };
+
+constexpr long SLAB_HALO = 8;          // >= 2K+1 = 7 rows a streaming pass recomputes per side
+
+// Row slab of `rank` at a level of size n cut over P ranks: even cuts (injection stays local), the
+// last rank also owns row n.  Pure arithmetic: every rank can compute every other rank's window.
+struct Slab { long own_lo, own_hi, mem_lo, mem_hi; };
+static Slab slab_of(long n, int P, int rank)
+{
+    Slab w;
+    const long per = n / P;
+    w.own_lo = rank * per;
+    w.own_hi = (rank + 1) * per - 1 + (rank == P - 1 ? 1 : 0);
+    w.mem_lo = w.own_lo - SLAB_HALO < 0 ? 0 : w.own_lo - SLAB_HALO;
+    w.mem_hi = w.own_hi + SLAB_HALO > n ? n : w.own_hi + SLAB_HALO;
+    return w;
+}
+// slab of the first agglomerated level on a non-root rank: the coarse rows under its fine slab
+static Slab child_slab_of(long n_fine, int P, int rank)
+{
+    const Slab f = slab_of(n_fine, P, rank);
+    const long nc = n_fine / 2;
+    Slab w;
+    w.own_lo = (f.own_lo + 1) / 2;
+    w.own_hi = f.own_hi / 2;
+    w.mem_lo = w.own_lo - SLAB_HALO < 0 ? 0 : w.own_lo - SLAB_HALO;
+    w.mem_hi = w.own_hi + SLAB_HALO > nc ? nc : w.own_hi + SLAB_HALO;
+    return w;
+}
 
 }  // namespace mgb200
 
@@ -86,6 +124,12 @@ struct mgb200_solver {
     long launches = 0;
     bool have_fields = false, have_rhs = false;
     double res0 = 0, res = 0;
+    // row-slab sharding (one process per GPU)
+    Comm* comm = nullptr;
+    int rank = 0, P = 1;
+    int last_sharded = -1;             // index of the coarsest sharded level (-1: none)
+    long shard_min_rows = 256;
+    double* d_top[3] = {nullptr, nullptr, nullptr};   // dense rows 0..N/4+1 of u0,v1,v2 (tower input when sharded)
 
     ~mgb200_solver() { release(); }
     void release();
@@ -100,6 +144,13 @@ struct mgb200_solver {
     int  form_rhs(double* res0_out);
     int  solve(mgb200_solve_info* info);
     int  get_u_natural(double* dst_dev, long ld);
+    int  alloc_levels();
+    int  alloc_top();
+    void fill_pass_window(StreamPassArgs& a, const Level& g, const Level& c) const;
+    int  exchange_halo(Level& g, double* a, Level* g2 = nullptr, double* a2 = nullptr);
+    int  gather_to_root(Level& c, double* arr);
+    int  scatter_from_root(Level& c, double* arr);
+    bool runs_level(int l) const { return P == 1 || rank == 0 || lv[l].sharded; }
     long count(long before) { long d = launch_counter() - before; launches += d; return d; }
 };
 
@@ -114,6 +165,8 @@ void mgb200_solver::release()
     cudaFree(d_norm2); d_norm2 = nullptr;
     cudaFree(d_coarse_iters); d_coarse_iters = nullptr;
     cudaFree(d_flat[0]); cudaFree(d_flat[1]); d_flat[0] = d_flat[1] = nullptr;
+    for (auto& t : d_top) { cudaFree(t); t = nullptr; }
+    if (comm) { comm_destroy(comm); comm = nullptr; }
     if (h_norm2) { cudaFreeHost(h_norm2); h_norm2 = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
 }
@@ -132,6 +185,9 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "coarsest level must have n <= 64 (on-device coarse solve); raise maxlvl");
     if (opt.shape < 1 || opt.niter < 0 || opt.max_cycle < 0 || opt.max_cycle > 50)
         return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
+    if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
+        return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
+    if (P > 1) opt.use_graph = 0;      // NCCL calls are issued directly on the stream
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MGB200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
@@ -146,13 +202,47 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
     MGB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     MGB_TRY(ops_basic_init());
     if (opt.plan == MGB200_PLAN_FUSED) MGB_TRY(stream_pass_init());
+    MGB_TRY(alloc_levels());
+    partials_cap = std::max(residual_partials_count(N), stream_pass_tiles(N, lv[0].own_hi - lv[0].own_lo + 1, -1)) + 8;
+    MGB_CUDA(cudaMalloc(&d_partials, partials_cap * sizeof(double)));
+    MGB_CUDA(cudaMalloc(&d_norm2, 8 * sizeof(double)));
+    MGB_CUDA(cudaMemsetAsync(d_norm2, 0, 8 * sizeof(double), stream));
+    MGB_CUDA(cudaMalloc(&d_coarse_iters, sizeof(int)));
+    MGB_CUDA(cudaMallocHost(&h_norm2, 8 * sizeof(double)));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    return MGB200_OK;
+}
+
+int mgb200_solver::alloc_levels()
+{
     lv.resize(maxlvl);
+    last_sharded = -1;
     for (int l = 0; l < maxlvl; ++l) {
         Level& g = lv[l];
-        g.n = n >> l;
+        g.n = N >> l;
         g.L = split_layout(g.n);
         g.st = make_stencil(dt, nu, dx * (double)(1L << l));    // dx2 = 2*dx per level (multigrid.cpp:49)
-        g.elems = layout_elems(g.L, g.n);
+        g.own_lo = 0; g.own_hi = g.n; g.mem_lo = 0; g.mem_hi = g.n; g.sharded = false; g.present = true;
+        if (P > 1) {
+            const bool can = l < maxlvl - 1 && (g.n / P) >= shard_min_rows && (g.n / P) >= 2 * SLAB_HALO && last_sharded == l - 1;
+            if (can) {
+                const Slab w = slab_of(g.n, P, rank);
+                g.own_lo = w.own_lo; g.own_hi = w.own_hi; g.mem_lo = w.mem_lo; g.mem_hi = w.mem_hi;
+                g.sharded = true;
+                last_sharded = l;
+            } else if (rank != 0) {
+                if (l == last_sharded + 1 && l > 0) {           // slab of the first agglomerated level
+                    const Slab w = child_slab_of(lv[l - 1].n, P, rank);
+                    g.own_lo = w.own_lo; g.own_hi = w.own_hi; g.mem_lo = w.mem_lo; g.mem_hi = w.mem_hi;
+                } else {
+                    g.present = false;
+                }
+            }
+        }
+        if (P > 1 && l == 0 && !g.sharded) return fail(MGB200_ERR_INVALID, "level 0 is too small to be cut over the ranks");
+        g.L.row0 = g.mem_lo;
+        if (!g.present) continue;
+        g.elems = (size_t)g.L.pitch * (size_t)g.rows_mem();
         const size_t bytes = g.elems * sizeof(double);
         MGB_CUDA(cudaMalloc(&g.u[0], bytes));
         MGB_CUDA(cudaMalloc(&g.u[1], bytes));
@@ -165,14 +255,85 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         MGB_CUDA(cudaMemsetAsync(g.v1, 0, bytes, stream));
         MGB_CUDA(cudaMemsetAsync(g.v2, 0, bytes, stream));
     }
-    partials_cap = std::max(residual_partials_count(N), stream_pass_tiles(N, N + 1, -1)) + 8;
-    MGB_CUDA(cudaMalloc(&d_partials, partials_cap * sizeof(double)));
-    MGB_CUDA(cudaMalloc(&d_norm2, 8 * sizeof(double)));
-    MGB_CUDA(cudaMemsetAsync(d_norm2, 0, 8 * sizeof(double), stream));
-    MGB_CUDA(cudaMalloc(&d_coarse_iters, sizeof(int)));
-    MGB_CUDA(cudaMallocHost(&h_norm2, 8 * sizeof(double)));
-    MGB_CUDA(cudaStreamSynchronize(stream));
     return MGB200_OK;
+}
+
+// dense rows 0..N/4+1 of the level-0 fields: all the reference's flat tower mapping ever reads
+int mgb200_solver::alloc_top()
+{
+    const size_t tb = (size_t)(N / 4 + 2) * (N + 1) * sizeof(double);
+    for (auto& t : d_top)
+        if (!t) MGB_CUDA(cudaMalloc(&t, tb));
+    return MGB200_OK;
+}
+
+void mgb200_solver::fill_pass_window(StreamPassArgs& a, const Level& g, const Level& c) const
+{
+    if (P == 1) return;                // rows_mem == 0: whole level
+    a.own_lo = g.own_lo; a.own_hi = g.own_hi;
+    a.row0 = g.mem_lo; a.rows_mem = g.rows_mem();
+    a.crow0 = c.mem_lo; a.crows_mem = c.rows_mem();
+}
+
+// Slab neighbours swap SLAB_HALO boundary rows of array `a` of level g (and optionally of a second
+// array of another sharded level) in one NCCL group.  Rows are contiguous: no packing.
+int mgb200_solver::exchange_halo(Level& g, double* a, Level* g2, double* a2)
+{
+    if (P == 1) return MGB200_OK;
+    P2P ops[8];
+    int n = 0;
+    Level* lvls[2] = {&g, g2};
+    double* arrs[2] = {a, a2};
+    for (int k = 0; k < 2; ++k) {
+        Level* q = lvls[k];
+        if (!q || !q->sharded) continue;
+        double* base = arrs[k];
+        const size_t cnt = (size_t)SLAB_HALO * q->L.pitch;
+        auto rowptr = [&](long row) { return base + (row - q->mem_lo) * q->L.pitch; };
+        if (rank > 0) {
+            ops[n++] = P2P{rank - 1, rowptr(q->own_lo), cnt, true};                 // my first rows -> upper neighbour
+            ops[n++] = P2P{rank - 1, rowptr(q->own_lo - SLAB_HALO), cnt, false};    // its last rows -> my upper halo
+        }
+        if (rank < P - 1) {
+            ops[n++] = P2P{rank + 1, rowptr(q->own_hi - SLAB_HALO + 1), cnt, true};
+            ops[n++] = P2P{rank + 1, rowptr(q->own_hi + 1), cnt, false};
+        }
+    }
+    return comm_p2p(comm, ops, n, stream);
+}
+
+// first agglomerated level: every rank's owned rows -> rank 0's whole array
+int mgb200_solver::gather_to_root(Level& c, double* arr)
+{
+    if (P == 1) return MGB200_OK;
+    const long nf = lv[last_sharded].n;
+    std::vector<P2P> ops;
+    if (rank == 0) {
+        for (int r = 1; r < P; ++r) {
+            const Slab w = child_slab_of(nf, P, r);
+            ops.push_back(P2P{r, arr + (w.own_lo - c.mem_lo) * c.L.pitch, (size_t)(w.own_hi - w.own_lo + 1) * c.L.pitch, false});
+        }
+    } else {
+        ops.push_back(P2P{0, arr + (c.own_lo - c.mem_lo) * c.L.pitch, (size_t)(c.own_hi - c.own_lo + 1) * c.L.pitch, true});
+    }
+    return comm_p2p(comm, ops.data(), (int)ops.size(), stream);
+}
+
+// rank 0's whole array -> every rank's slab window (own rows + halo) of the first agglomerated level
+int mgb200_solver::scatter_from_root(Level& c, double* arr)
+{
+    if (P == 1) return MGB200_OK;
+    const long nf = lv[last_sharded].n;
+    std::vector<P2P> ops;
+    if (rank == 0) {
+        for (int r = 1; r < P; ++r) {
+            const Slab w = child_slab_of(nf, P, r);
+            ops.push_back(P2P{r, arr + (w.mem_lo - c.mem_lo) * c.L.pitch, (size_t)(w.mem_hi - w.mem_lo + 1) * c.L.pitch, true});
+        }
+    } else {
+        ops.push_back(P2P{0, arr, (size_t)c.rows_mem() * c.L.pitch, false});
+    }
+    return comm_p2p(comm, ops.data(), (int)ops.size(), stream);
 }
 
 // Coarse velocity towers (timestepper prologue, multigrid.cpp:148-160).
@@ -192,15 +353,21 @@ int mgb200_solver::build_towers()
     const size_t fb = (size_t)(h + 1) * (h + 1) * sizeof(double);
     for (int k = 0; k < 2; ++k)
         if (!d_flat[k]) MGB_CUDA(cudaMalloc(&d_flat[k], fb));
+    // The flat mapping only reads rows 0..N/4+1 of the level-0 velocity.  A single GPU reads them
+    // from its own level 0; a slab rank from the dense copy of those rows that set_fields left in
+    // d_top (every rank builds every flat buffer redundantly and keeps the rows of its windows).
     for (int which = 0; which < 2; ++which) {
-        const double* src0 = which == 0 ? lv[0].v1 : lv[0].v2;
+        const double* src0 = P == 1 ? (which == 0 ? lv[0].v1 : lv[0].v2) : d_top[1 + which];
+        const Layout L0 = P == 1 ? lv[0].L : natural_layout(N + 1);
         int cur = 0;
         for (int l = 1; l < maxlvl; ++l) {
             MGB_CUDA(cudaMemsetAsync(d_flat[cur], 0, fb, stream));
-            if (l == 1) MGB_TRY(launch_tower_flat(d_flat[cur], src0, true, lv[0].L, N, stream));
-            else MGB_TRY(launch_tower_flat(d_flat[cur], d_flat[1 - cur], false, lv[0].L, N, stream));
-            double* dst = which == 0 ? lv[l].v1 : lv[l].v2;
-            MGB_TRY(launch_flat_to_level(dst, lv[l].L, d_flat[cur], lv[l].n, stream));
+            if (l == 1) MGB_TRY(launch_tower_flat(d_flat[cur], src0, true, L0, N, stream));
+            else MGB_TRY(launch_tower_flat(d_flat[cur], d_flat[1 - cur], false, L0, N, stream));
+            if (lv[l].present) {
+                double* dst = which == 0 ? lv[l].v1 : lv[l].v2;
+                MGB_TRY(launch_flat_to_level(dst, lv[l].L, d_flat[cur], lv[l].n, stream, lv[l].mem_lo, lv[l].mem_hi));
+            }
             cur = 1 - cur;
         }
     }
@@ -221,6 +388,7 @@ int mgb200_solver::smooth(Level& g, int iters)
 int mgb200_solver::cycle_body(int l)
 {
     Level& g = lv[l];
+    const bool split = P > 1 && g.sharded;                                        // this level is cut over the ranks
     for (int rep = 0; rep < opt.shape; ++rep) {                                   // multigrid.cpp:52
         if (l == maxlvl - 1) {
             // coarsest level: on-device loop {GS; residual; norm} (multigrid.cpp:55-65).  A level
@@ -257,11 +425,20 @@ int mgb200_solver::cycle_body(int l)
                 a.iters = k;
                 a.Lc = c.L;
                 if (left == 0) { a.post = POST_INJECT; a.coarse_rhs = c.rhs; }
+                fill_pass_window(a, g, c);
                 MGB_TRY(stream_pass(a, stream));
                 g.cur = 1 - g.cur;
                 first = false;
+                if (split && left > 0) MGB_TRY(exchange_halo(g, g.u[g.cur]));
             } while (left > 0);
-            MGB_TRY(cycle_body(l + 1));
+            if (split) {
+                // the new iterate's halo rows (read by the up leg) and the coarse right-hand side:
+                // halo rows to the slab neighbours, or everything to rank 0 if the child is agglomerated
+                if (c.sharded) MGB_TRY(exchange_halo(g, g.u[g.cur], &c, c.rhs));
+                else { MGB_TRY(exchange_halo(g, g.u[g.cur])); MGB_TRY(gather_to_root(c, c.rhs)); }
+            }
+            if (runs_level(l + 1)) MGB_TRY(cycle_body(l + 1));
+            if (split && !c.sharded) MGB_TRY(scatter_from_root(c, c.u[c.cur]));
             // ---- up leg: prolong + correct, niter RB iterations (+ residual norm on level 0) ----
             left = opt.niter;
             first = true;
@@ -277,9 +454,11 @@ int mgb200_solver::cycle_body(int l)
                 a.Lc = c.L;
                 if (first) a.coarse_u = c.u[c.cur];
                 if (left == 0 && l == 0 && rep == opt.shape - 1) { a.post = POST_NORM2; a.partials = d_partials; }
+                fill_pass_window(a, g, c);
                 MGB_TRY(stream_pass(a, stream));
                 g.cur = 1 - g.cur;
                 first = false;
+                if (split) MGB_TRY(exchange_halo(g, g.u[g.cur]));
             } while (left > 0);
         }
     }
@@ -301,7 +480,8 @@ int mgb200_solver::record_cycle()
     if (opt.plan == MGB200_PLAN_FUSED && maxlvl > 1) {
         // the level-0 up leg already produced the per-tile sums of squares (its LAST chunk did)
         const int last_k = opt.niter == 0 ? 0 : ((opt.niter - 1) % 3) + 1;
-        MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, N + 1, last_k), d_norm2, stream));
+        MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, lv[0].own_hi - lv[0].own_lo + 1, last_k), d_norm2, stream));
+        MGB_TRY(comm_allreduce_sum(comm, d_norm2, 1, stream));
     } else {
         MGB_TRY(residual_norm_level0());
     }
@@ -357,8 +537,16 @@ int mgb200_solver::form_rhs(double* res0_out)
     if (!have_fields) return fail(MGB200_ERR_STATE, "form_rhs before set_fields");
     Level& g = lv[0];
     const long before = launch_counter();
-    MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream));
-    MGB_TRY(launch_reduce_partials(d_partials, residual_partials_count(g.n), d_norm2, stream));
+    if (P == 1) {
+        MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream));
+        MGB_TRY(launch_reduce_partials(d_partials, residual_partials_count(g.n), d_norm2, stream));
+    } else {
+        const long ilo = g.own_lo < 1 ? 1 : g.own_lo, ihi = g.own_hi > g.n - 1 ? g.n - 1 : g.own_hi;
+        MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream, ilo, ihi));
+        MGB_TRY(launch_reduce_partials(d_partials, rows_partials_count(g.n, ihi - ilo + 1), d_norm2, stream));
+        MGB_TRY(comm_allreduce_sum(comm, d_norm2, 1, stream));
+        MGB_TRY(exchange_halo(g, g.rhs));
+    }
     count(before);
     have_rhs = true;
     MGB_TRY(read_norm(&res0));
@@ -386,7 +574,8 @@ int mgb200_solver::get_u_natural(double* dst_dev, long ld)
 {
     Level& g = lv[0];
     const long before = launch_counter();
-    MGB_TRY(launch_convert(dst_dev, natural_layout(ld), g.u[g.cur], g.L, g.n, stream));
+    // a slab rank fills its own rows only (the destination is a full-size array)
+    MGB_TRY(launch_convert(dst_dev, natural_layout(ld), g.u[g.cur], g.L, g.n, stream, g.own_lo, g.own_hi));
     count(before);
     return MGB200_OK;
 }
@@ -427,6 +616,67 @@ int mgb200_create(mgb200_solver** out, long n, int maxlvl, double nu, double dt,
     return MGB200_OK;
 }
 
+int mgb200_comm_unique_id(unsigned char id[128]) { return comm_unique_id(id); }
+
+int mgb200_create_sharded(mgb200_solver** out, long n, int maxlvl, double nu, double dt, double dx, double tol,
+                          const mgb200_options* opt, int rank, int nranks, const unsigned char id[128], long shard_min_rows)
+{
+    if (!out) return fail(MGB200_ERR_INVALID, "out == NULL");
+    *out = nullptr;
+    if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks)
+        return fail(MGB200_ERR_INVALID, "create_sharded: nranks must be a power of two, 0 <= rank < nranks");
+    mgb200_solver* s = new mgb200_solver();
+    s->rank = rank; s->P = nranks;
+    if (shard_min_rows > 0) s->shard_min_rows = shard_min_rows;
+    int rc = MGB200_OK;
+    if (nranks > 1) {
+        if (opt && opt->device >= 0) cudaSetDevice(opt->device);   // the communicator binds to the current device
+        rc = comm_create(&s->comm, rank, nranks, id);
+    }
+    if (rc == MGB200_OK) rc = s->init(n, maxlvl, nu, dt, dx, tol, opt);
+    if (rc != MGB200_OK) { delete s; return rc; }
+    *out = s;
+    return MGB200_OK;
+}
+
+int mgb200_slab_plan(long n, int maxlvl, int nranks, int rank, long shard_min_rows, int lvl, long out[6])
+{
+    // pure arithmetic (no GPU): the row window of `rank` at level `lvl` under the sharding rule of
+    // alloc_levels.  out = {sharded, present, own_lo, own_hi, mem_lo, mem_hi}
+    if (!out || lvl < 0 || lvl >= maxlvl || nranks < 1 || rank < 0 || rank >= nranks) return fail(MGB200_ERR_INVALID, "slab_plan: bad argument");
+    if (shard_min_rows <= 0) shard_min_rows = 256;
+    int last = -1;
+    for (int l = 0; l <= lvl; ++l) {
+        const long nl = n >> l;
+        long w[6] = {0, 1, 0, nl, 0, nl};
+        if (nranks > 1) {
+            const bool can = l < maxlvl - 1 && (nl / nranks) >= shard_min_rows && (nl / nranks) >= 2 * SLAB_HALO && last == l - 1;
+            if (can) {
+                const Slab q = slab_of(nl, nranks, rank);
+                w[0] = 1; w[2] = q.own_lo; w[3] = q.own_hi; w[4] = q.mem_lo; w[5] = q.mem_hi;
+                last = l;
+            } else if (rank != 0) {
+                if (l == last + 1 && l > 0) {
+                    const Slab q = child_slab_of(n >> (l - 1), nranks, rank);
+                    w[2] = q.own_lo; w[3] = q.own_hi; w[4] = q.mem_lo; w[5] = q.mem_hi;
+                } else {
+                    w[1] = 0;
+                }
+            }
+        }
+        if (l == lvl) std::memcpy(out, w, sizeof(w));
+    }
+    return MGB200_OK;
+}
+
+int mgb200_slab(mgb200_solver* s, int lvl, long out[6])
+{
+    if (!s || !out || lvl < 0 || lvl >= s->maxlvl) return fail(MGB200_ERR_INVALID, "slab: bad argument");
+    const Level& g = s->lv[lvl];
+    out[0] = g.sharded; out[1] = g.present; out[2] = g.own_lo; out[3] = g.own_hi; out[4] = g.mem_lo; out[5] = g.mem_hi;
+    return MGB200_OK;
+}
+
 int mgb200_destroy(mgb200_solver* s)
 {
     if (!s) return MGB200_OK;
@@ -439,6 +689,11 @@ int mgb200_destroy(mgb200_solver* s)
 static int after_fields(mgb200_solver* s)
 {
     MGB_TRY(s->build_towers());
+    if (s->P > 1) {                    // the tower inputs are no longer needed
+        MGB_CUDA(cudaStreamSynchronize(s->stream));
+        for (auto& t : s->d_top) { cudaFree(t); t = nullptr; }
+        cudaFree(s->d_flat[0]); cudaFree(s->d_flat[1]); s->d_flat[0] = s->d_flat[1] = nullptr;
+    }
     s->have_fields = true;
     s->have_rhs = false;
     return MGB200_OK;
@@ -449,9 +704,16 @@ int mgb200_set_fields_device(mgb200_solver* s, const double* u0, const double* v
     if (!s || !u0 || !v1 || !v2 || ld < s->N + 1) return fail(MGB200_ERR_INVALID, "set_fields_device: bad argument");
     Level& g = s->lv[0];
     const long before = launch_counter();
-    MGB_TRY(launch_convert(g.u[g.cur], g.L, u0, natural_layout(ld), g.n, s->stream));
-    MGB_TRY(launch_convert(g.v1, g.L, v1, natural_layout(ld), g.n, s->stream));
-    MGB_TRY(launch_convert(g.v2, g.L, v2, natural_layout(ld), g.n, s->stream));
+    // (slab ranks take the rows of their window out of the full-size arrays)
+    MGB_TRY(launch_convert(g.u[g.cur], g.L, u0, natural_layout(ld), g.n, s->stream, g.mem_lo, g.mem_hi));
+    MGB_TRY(launch_convert(g.v1, g.L, v1, natural_layout(ld), g.n, s->stream, g.mem_lo, g.mem_hi));
+    MGB_TRY(launch_convert(g.v2, g.L, v2, natural_layout(ld), g.n, s->stream, g.mem_lo, g.mem_hi));
+    if (s->P > 1) {
+        MGB_TRY(s->alloc_top());
+        const long top = s->N / 4 + 1;
+        MGB_TRY(launch_convert(s->d_top[1], natural_layout(s->N + 1), v1, natural_layout(ld), s->N, s->stream, 0, top));
+        MGB_TRY(launch_convert(s->d_top[2], natural_layout(s->N + 1), v2, natural_layout(ld), s->N, s->stream, 0, top));
+    }
     MGB_TRY(after_fields(s));
     s->count(before);
     MGB_CUDA(cudaStreamSynchronize(s->stream));     // the caller may free its arrays on return
@@ -463,20 +725,28 @@ int mgb200_set_fields_host(mgb200_solver* s, const double* u0, const double* v1,
     if (!s || !u0 || !v1 || !v2) return fail(MGB200_ERR_INVALID, "set_fields_host: bad argument");
     Level& g = s->lv[0];
     const long n = g.n;
-    const size_t bytes = (size_t)(n + 1) * (n + 1) * sizeof(double);
-    const Layout dense = natural_layout(n + 1);
-    // two staging areas (both larger than a dense field): the idle twin of u and the rhs array
+    // rows of this rank's window (all rows on a single GPU), dense in the host arrays
+    const size_t off = (size_t)g.mem_lo * (n + 1);
+    const size_t bytes = (size_t)g.rows_mem() * (n + 1) * sizeof(double);
+    const Layout dense = natural_layout(n + 1, g.mem_lo);
+    // two staging areas (both larger than a dense window): the idle twin of u and the rhs array
     double* stage_a = g.u[1 - g.cur];
     double* stage_b = g.rhs;
     const long before = launch_counter();
-    MGB_CUDA(cudaMemcpyAsync(stage_a, u0, bytes, cudaMemcpyHostToDevice, s->stream));
-    MGB_TRY(launch_convert(g.u[g.cur], g.L, stage_a, dense, n, s->stream));
-    MGB_CUDA(cudaMemcpyAsync(stage_b, v1, bytes, cudaMemcpyHostToDevice, s->stream));
-    MGB_TRY(launch_convert(g.v1, g.L, stage_b, dense, n, s->stream));
-    MGB_CUDA(cudaMemcpyAsync(stage_a, v2, bytes, cudaMemcpyHostToDevice, s->stream));
-    MGB_TRY(launch_convert(g.v2, g.L, stage_a, dense, n, s->stream));
+    MGB_CUDA(cudaMemcpyAsync(stage_a, u0 + off, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.u[g.cur], g.L, stage_a, dense, n, s->stream, g.mem_lo, g.mem_hi));
+    MGB_CUDA(cudaMemcpyAsync(stage_b, v1 + off, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.v1, g.L, stage_b, dense, n, s->stream, g.mem_lo, g.mem_hi));
+    MGB_CUDA(cudaMemcpyAsync(stage_a, v2 + off, bytes, cudaMemcpyHostToDevice, s->stream));
+    MGB_TRY(launch_convert(g.v2, g.L, stage_a, dense, n, s->stream, g.mem_lo, g.mem_hi));
     MGB_CUDA(cudaMemsetAsync(stage_a, 0, g.elems * sizeof(double), s->stream));
     MGB_CUDA(cudaMemsetAsync(stage_b, 0, g.elems * sizeof(double), s->stream));
+    if (s->P > 1) {
+        MGB_TRY(s->alloc_top());
+        const size_t tb = (size_t)(s->N / 4 + 2) * (n + 1) * sizeof(double);
+        MGB_CUDA(cudaMemcpyAsync(s->d_top[1], v1, tb, cudaMemcpyHostToDevice, s->stream));
+        MGB_CUDA(cudaMemcpyAsync(s->d_top[2], v2, tb, cudaMemcpyHostToDevice, s->stream));
+    }
     MGB_TRY(after_fields(s));
     s->count(before);
     MGB_CUDA(cudaStreamSynchronize(s->stream));
@@ -488,7 +758,11 @@ int mgb200_set_fields_reference_ic(mgb200_solver* s, double vscale)
     if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
     Level& g = s->lv[0];
     const long before = launch_counter();
-    MGB_TRY(launch_initial_conditions(g.u[g.cur], g.v1, g.v2, g.n, g.L, vscale, s->stream));
+    MGB_TRY(launch_initial_conditions(g.u[g.cur], g.v1, g.v2, g.n, g.L, vscale, s->stream, g.mem_lo, g.mem_hi));
+    if (s->P > 1) {
+        MGB_TRY(s->alloc_top());
+        MGB_TRY(launch_initial_conditions(s->d_top[0], s->d_top[1], s->d_top[2], g.n, natural_layout(g.n + 1), vscale, s->stream, 0, s->N / 4 + 1));
+    }
     MGB_TRY(after_fields(s));
     s->count(before);
     return MGB200_OK;
@@ -548,9 +822,15 @@ int mgb200_get_u_host(mgb200_solver* s, double* u)
     if (!s || !u) return fail(MGB200_ERR_INVALID, "get_u_host: bad argument");
     Level& g = s->lv[0];
     double* stage = g.u[1 - g.cur];      // idle between passes
-    MGB_TRY(s->get_u_natural(stage, g.n + 1));
-    MGB_CUDA(cudaMemcpyAsync(u, stage, (size_t)(g.n + 1) * (g.n + 1) * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    // dense staging of the OWNED rows (a slab rank fills only its rows of the full-size host array)
+    const long before = launch_counter();
+    MGB_TRY(launch_convert(stage, natural_layout(g.n + 1, g.own_lo), g.u[g.cur], g.L, g.n, s->stream, g.own_lo, g.own_hi));
+    s->count(before);
+    MGB_CUDA(cudaMemcpyAsync(u + (size_t)g.own_lo * (g.n + 1), stage, (size_t)(g.own_hi - g.own_lo + 1) * (g.n + 1) * sizeof(double),
+                             cudaMemcpyDeviceToHost, s->stream));
     MGB_CUDA(cudaStreamSynchronize(s->stream));
+    // the staging buffer doubles as the next pass's output: restore its boundary rows/columns later? not needed:
+    // every pass rewrites all owned rows of its output, and the halo rows are refreshed by the exchange
     return MGB200_OK;
 }
 
@@ -558,11 +838,14 @@ int mgb200_get_level_host(mgb200_solver* s, int lvl, int which, double* out)
 {
     if (!s || !out || lvl < 0 || lvl >= s->maxlvl || which < 0 || which > 3) return fail(MGB200_ERR_INVALID, "get_level_host: bad argument");
     Level& g = s->lv[lvl];
+    if (!g.present) return MGB200_OK;    // nothing of this level lives on this rank
     const double* src = which == 0 ? g.u[g.cur] : which == 1 ? g.rhs : which == 2 ? g.v1 : g.v2;
     double* tmp = nullptr;
-    const size_t bytes = (size_t)(g.n + 1) * (g.n + 1) * sizeof(double);
+    // the rows held by this rank (all rows on a single GPU) land in their place of the full-size array
+    const size_t bytes = (size_t)g.rows_mem() * (g.n + 1) * sizeof(double);
+    out += (size_t)g.mem_lo * (g.n + 1);
     MGB_CUDA(cudaMalloc(&tmp, bytes));
-    int rc = launch_convert(tmp, natural_layout(g.n + 1), src, g.L, g.n, s->stream);
+    int rc = launch_convert(tmp, natural_layout(g.n + 1, g.mem_lo), src, g.L, g.n, s->stream, g.mem_lo, g.mem_hi);
     if (rc == MGB200_OK) {
         cudaError_t e = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -616,7 +899,7 @@ int mgb200_profile_level0(mgb200_solver* s, int reps, double* ms_a, double* byte
     if (s->maxlvl < 2) return fail(MGB200_ERR_INVALID, "profile_level0: needs at least two levels");
     Level& g = s->lv[0];
     Level& c = s->lv[1];
-    const double m0 = (double)(g.n + 1) * (double)(g.n + 1);
+    const double m0 = (double)(g.own_hi - g.own_lo + 1) * (double)(g.n + 1);   // nodes this rank produces
     cudaEvent_t e0, e1;
     MGB_CUDA(cudaEventCreate(&e0));
     MGB_CUDA(cudaEventCreate(&e1));
@@ -635,6 +918,7 @@ int mgb200_profile_level0(mgb200_solver* s, int reps, double* ms_a, double* byte
                 a.Lc = c.L;
                 if (which == 0) { a.post = POST_INJECT; a.coarse_rhs = c.rhs; }
                 else { a.coarse_u = c.u[c.cur]; a.post = POST_NORM2; a.partials = s->d_partials; }
+                s->fill_pass_window(a, g, c);
                 rc = stream_pass(a, s->stream);
                 g.cur = 1 - g.cur;
             } else if (which == 0) {

@@ -142,6 +142,27 @@ int mgb200_create(mgb200_solver **out, long n, int maxlvl, double nu, double dt,
                   double tol, const mgb200_options *opt);
 int mgb200_destroy(mgb200_solver *s);
 
+/* ------------------------------------------------------------------------------------------
+ * Row-slab sharding over the GPUs of one node, one process per GPU (no reference counterpart: the
+ * reference is single-GPU).  Rank 0 calls mgb200_comm_unique_id and the host
+ * program broadcasts the 128 bytes (bench.py uses torch.distributed); every rank then calls
+ * mgb200_create_sharded on its own device.  Fine levels are cut into row slabs at even rows (own
+ * rows + 8 halo rows exchanged with the slab neighbours over NCCL after every streaming pass); levels
+ * with fewer than shard_min_rows rows per rank (0 = default 256) run whole on rank 0, fed by a
+ * gather of the restricted residual and followed by a scatter of the correction; the residual norm
+ * is all-reduced.  The handle is then used like a single-GPU one: set_fields_* take the FULL-SIZE
+ * arrays on every rank (each rank keeps its window), get_u_* fill only the rows the rank owns.
+ * Fused plan only; CUDA-graph replay is off (NCCL calls go straight to the stream).
+ * ------------------------------------------------------------------------------------------ */
+int mgb200_comm_unique_id(unsigned char id[128]);
+int mgb200_create_sharded(mgb200_solver **out, long n, int maxlvl, double nu, double dt, double dx,
+                          double tol, const mgb200_options *opt, int rank, int nranks,
+                          const unsigned char id[128], long shard_min_rows);
+/* the handle's row window at a level: out = {sharded, present, own_lo, own_hi, mem_lo, mem_hi} */
+int mgb200_slab(mgb200_solver *s, int lvl, long out[6]);
+/* the same rule as pure arithmetic (no GPU needed): window of `rank` of `nranks` at level lvl */
+int mgb200_slab_plan(long n, int maxlvl, int nranks, int rank, long shard_min_rows, int lvl, long out[6]);
+
 /* copy u0, v1, v2 in (dense (n+1)^2 DEVICE arrays, row stride ld) and build the level towers
  * (timestepper prologue, multigrid.cpp:138-160) */
 int mgb200_set_fields_device(mgb200_solver *s, const double *u0, const double *v1,
