@@ -13,6 +13,7 @@
 // pinned memory.  The coarsest level is solved by one thread block on the device
 // (multigrid.cpp:55-65), so no host round trip happens inside a cycle.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -187,7 +188,8 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
-    if (P > 1) opt.use_graph = 0;      // NCCL calls are issued directly on the stream
+    // NCCL calls are issued directly on the stream unless graph capture of them is asked for
+    if (P > 1 && !getenv("MGB200_SHARDED_GRAPH")) opt.use_graph = 0;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MGB200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
