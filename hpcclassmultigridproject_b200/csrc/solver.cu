@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "comm.cuh"
@@ -131,6 +133,32 @@ struct mgb200_solver {
     int last_sharded = -1;             // index of the coarsest sharded level (-1: none)
     long shard_min_rows = 256;
     double* d_top[3] = {nullptr, nullptr, nullptr};   // dense rows 0..N/4+1 of u0,v1,v2 (tower input when sharded)
+    // MGB200_TRACE=1: CUDA events between the phases of a cycle, printed by rank 0 (diagnostics)
+    bool tracing = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const std::string& name)
+    {
+        if (!tracing) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream);
+        marks.emplace_back(name, e);
+    }
+    void dump_marks()
+    {
+        if (!tracing || marks.empty()) return;
+        cudaStreamSynchronize(stream);
+        if (rank == 0) {
+            std::string line = "MGB200_TRACE";
+            for (size_t k = 1; k < marks.size(); ++k) {
+                float ms = 0; cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+                char buf[96]; snprintf(buf, sizeof buf, " | %s %.3f", marks[k].first.c_str(), ms);
+                line += buf;
+            }
+            float tot = 0; cudaEventElapsedTime(&tot, marks.front().second, marks.back().second);
+            fprintf(stderr, "%s | total %.3f ms\n", line.c_str(), tot);
+        }
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
 
     ~mgb200_solver() { release(); }
     void release();
@@ -190,6 +218,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
     // NCCL calls are issued directly on the stream unless graph capture of them is asked for
     if (P > 1 && !getenv("MGB200_SHARDED_GRAPH")) opt.use_graph = 0;
+    if (getenv("MGB200_TRACE")) { tracing = true; opt.use_graph = 0; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MGB200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
@@ -433,14 +462,16 @@ int mgb200_solver::cycle_body(int l)
                 first = false;
                 if (split && left > 0) MGB_TRY(exchange_halo(g, g.u[g.cur]));
             } while (left > 0);
+            mark("L" + std::to_string(l) + "dn");
             if (split) {
                 // the new iterate's halo rows (read by the up leg) and the coarse right-hand side:
                 // halo rows to the slab neighbours, or everything to rank 0 if the child is agglomerated
                 if (c.sharded) MGB_TRY(exchange_halo(g, g.u[g.cur], &c, c.rhs));
                 else { MGB_TRY(exchange_halo(g, g.u[g.cur])); MGB_TRY(gather_to_root(c, c.rhs)); }
             }
+            mark("L" + std::to_string(l) + "x");
             if (runs_level(l + 1)) MGB_TRY(cycle_body(l + 1));
-            if (split && !c.sharded) MGB_TRY(scatter_from_root(c, c.u[c.cur]));
+            if (split && !c.sharded) { mark("sub"); MGB_TRY(scatter_from_root(c, c.u[c.cur])); mark("scat"); }
             // ---- up leg: prolong + correct, niter RB iterations (+ residual norm on level 0) ----
             left = opt.niter;
             first = true;
@@ -460,7 +491,8 @@ int mgb200_solver::cycle_body(int l)
                 MGB_TRY(stream_pass(a, stream));
                 g.cur = 1 - g.cur;
                 first = false;
-                if (split) MGB_TRY(exchange_halo(g, g.u[g.cur]));
+                mark("L" + std::to_string(l) + "up");
+                if (split) { MGB_TRY(exchange_halo(g, g.u[g.cur])); mark("L" + std::to_string(l) + "x"); }
             } while (left > 0);
         }
     }
@@ -478,12 +510,14 @@ int mgb200_solver::residual_norm_level0()
 
 int mgb200_solver::record_cycle()
 {
+    mark("start");
     MGB_TRY(cycle_body(0));
     if (opt.plan == MGB200_PLAN_FUSED && maxlvl > 1) {
         // the level-0 up leg already produced the per-tile sums of squares (its LAST chunk did)
         const int last_k = opt.niter == 0 ? 0 : ((opt.niter - 1) % 3) + 1;
         MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, lv[0].own_hi - lv[0].own_lo + 1, last_k), d_norm2, stream));
         MGB_TRY(comm_allreduce_sum(comm, d_norm2, 1, stream));
+        mark("norm");
     } else {
         MGB_TRY(residual_norm_level0());
     }
@@ -497,6 +531,7 @@ int mgb200_solver::run_cycle_async()
         const long before = launch_counter();
         MGB_TRY(record_cycle());
         count(before);
+        dump_marks();
         return MGB200_OK;
     }
     if (!graph_exec) {
