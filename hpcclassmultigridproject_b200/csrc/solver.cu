@@ -216,8 +216,9 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
-    // NCCL calls are issued directly on the stream unless graph capture of them is asked for
-    if (P > 1 && !getenv("MGB200_SHARDED_GRAPH")) opt.use_graph = 0;
+    // the sharded cycle (kernels + NCCL point-to-point groups + all-reduce) is captured like the
+    // single-GPU one; MGB200_SHARDED_GRAPH=0 issues everything directly on the stream instead
+    if (P > 1) { const char* e = getenv("MGB200_SHARDED_GRAPH"); if (e && atoi(e) == 0) opt.use_graph = 0; }
     if (getenv("MGB200_TRACE")) { tracing = true; opt.use_graph = 0; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

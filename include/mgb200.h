@@ -152,7 +152,7 @@ int mgb200_destroy(mgb200_solver *s);
  * gather of the restricted residual and followed by a scatter of the correction; the residual norm
  * is all-reduced.  The handle is then used like a single-GPU one: set_fields_* take the FULL-SIZE
  * arrays on every rank (each rank keeps its window), get_u_* fill only the rows the rank owns.
- * Fused plan only; CUDA-graph replay is off (NCCL calls go straight to the stream).
+ * Fused plan only.  The whole sharded cycle, NCCL calls included, is captured into the CUDA graph.
  * ------------------------------------------------------------------------------------------ */
 int mgb200_comm_unique_id(unsigned char id[128]);
 int mgb200_create_sharded(mgb200_solver **out, long n, int maxlvl, double nu, double dt, double dx,
