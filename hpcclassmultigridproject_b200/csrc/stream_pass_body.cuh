@@ -342,10 +342,19 @@ SP_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem&
         o0 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a0, b0), a1), b1), 0.25);              // gs.cpp:241
         o1 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a1, b1), a2), b2), 0.25);
     }
-    if (st.ok_cur & 4u) sp_sts1(sm, st.a_cur, __dadd_rn(ue.x, e0));                         // multigrid.cpp:83
-    if (st.ok_cur & 8u) sp_sts1(sm, st.a_cur + 8u, __dadd_rn(ue.y, e1));
-    if (st.ok_cur & 1u) sp_sts1(sm, st.a_cur + geo.swkb, __dadd_rn(uo.x, o0));
-    if (st.ok_cur & 2u) sp_sts1(sm, st.a_cur + geo.swkb + 8u, __dadd_rn(uo.y, o1));
+    // multigrid.cpp:83.  16-byte stores in the common case (8-byte stores at a 16-byte lane stride
+    // cost twice the shared-memory wavefronts)
+    const double ne0 = __dadd_rn(ue.x, e0), ne1 = __dadd_rn(ue.y, e1), no0 = __dadd_rn(uo.x, o0), no1 = __dadd_rn(uo.y, o1);
+    if ((st.ok_cur & 12u) == 12u) sp_sts2(sm, st.a_cur, D2{ne0, ne1});
+    else {
+        if (st.ok_cur & 4u) sp_sts1(sm, st.a_cur, ne0);
+        if (st.ok_cur & 8u) sp_sts1(sm, st.a_cur + 8u, ne1);
+    }
+    if ((st.ok_cur & 3u) == 3u) sp_sts2(sm, st.a_cur + geo.swkb, D2{no0, no1});
+    else {
+        if (st.ok_cur & 1u) sp_sts1(sm, st.a_cur + geo.swkb, no0);
+        if (st.ok_cur & 2u) sp_sts1(sm, st.a_cur + geo.swkb + 8u, no1);
+    }
 }
 
 // residual epilogue on finished row q, one node per lane (PAR = its column parity): injection into
