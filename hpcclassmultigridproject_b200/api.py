@@ -85,6 +85,7 @@ def lib():
     L.mgb200_timestepper_host.argtypes = [_vp, _vp, _vp, _vp, _d, _i, _i, _d, _d, _d, _d, _i, C.POINTER(Options),
                                           C.POINTER(SolveInfo)]
     L.mgb200_timestepper_device.argtypes = L.mgb200_timestepper_host.argtypes
+    L.mgb200_release_cached.argtypes = []
     _lib = L
     return L
 
@@ -301,6 +302,11 @@ class Solver:
     @property
     def cycle_bytes(self) -> float:
         return lib().mgb200_cycle_bytes(self.h)
+
+
+def release_cached():
+    """free the handle the one-call drivers keep between calls"""
+    _ck(lib().mgb200_release_cached())
 
 
 def timestepper_host(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape=1, **opts):

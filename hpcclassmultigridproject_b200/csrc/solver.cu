@@ -867,8 +867,8 @@ int mgb200_get_u_host(mgb200_solver* s, double* u)
     MGB_CUDA(cudaMemcpyAsync(u + (size_t)g.own_lo * (g.n + 1), stage, (size_t)(g.own_hi - g.own_lo + 1) * (g.n + 1) * sizeof(double),
                              cudaMemcpyDeviceToHost, s->stream));
     MGB_CUDA(cudaStreamSynchronize(s->stream));
-    // the staging buffer doubles as the next pass's output: restore its boundary rows/columns later? not needed:
-    // every pass rewrites all owned rows of its output, and the halo rows are refreshed by the exchange
+    // (the staging buffer is the next pass's output: every pass rewrites all owned rows of its output
+    // and the exchange refreshes the halo rows, so nothing needs restoring)
     return MGB200_OK;
 }
 
@@ -983,6 +983,20 @@ int mgb200_profile_level0(mgb200_solver* s, int reps, double* ms_a, double* byte
     return MGB200_OK;
 }
 
+// The reference's timestepper allocates and frees its towers on every call (multigrid.cpp:138-162,
+// 177-185).  Allocating and zero-filling ~14 GB of HBM per call would dominate an N=16384 call, so
+// the one-call drivers keep the last handle alive and reuse it when the next call has the same
+// shape and parameters; mgb200_release_cached() frees it.
+namespace {
+struct CachedHandle {
+    std::mutex mu;
+    mgb200_solver* s = nullptr;
+    long n = 0; int maxlvl = 0; double nu = 0, dt = 0, dx = 0, tol = 0;
+    mgb200_options opt{};
+};
+CachedHandle g_cached;
+}  // namespace
+
 static int timestepper_common(double* uT, const double* u0, const double* v1, const double* v2, double nu, int maxlvl,
                               int n, double dt, double T, double dx, double tol, int shape, const mgb200_options* opt,
                               mgb200_solve_info* last, bool host)
@@ -990,8 +1004,17 @@ static int timestepper_common(double* uT, const double* u0, const double* v1, co
     mgb200_options o;
     if (opt) o = *opt; else mgb200_default_options(&o);
     o.shape = shape;
-    mgb200_solver* s = nullptr;
-    MGB_TRY(mgb200_create(&s, n, maxlvl, nu, dt, dx, tol, &o));
+    std::lock_guard<std::mutex> lock(g_cached.mu);
+    const bool reuse = g_cached.s && g_cached.n == n && g_cached.maxlvl == maxlvl && g_cached.nu == nu && g_cached.dt == dt &&
+                       g_cached.dx == dx && g_cached.tol == tol && std::memcmp(&g_cached.opt, &o, sizeof(o)) == 0;
+    if (!reuse) {
+        if (g_cached.s) { mgb200_destroy(g_cached.s); g_cached.s = nullptr; }
+        MGB_TRY(mgb200_create(&g_cached.s, n, maxlvl, nu, dt, dx, tol, &o));
+        g_cached.n = n; g_cached.maxlvl = maxlvl; g_cached.nu = nu; g_cached.dt = dt; g_cached.dx = dx; g_cached.tol = tol;
+        g_cached.opt = o;
+    }
+    mgb200_solver* s = g_cached.s;
+    MGB_CUDA(cudaSetDevice(s->device));
     int rc = host ? mgb200_set_fields_host(s, u0, v1, v2) : mgb200_set_fields_device(s, u0, v1, v2, n + 1);
     const int nsteps = (int)(T / dt);                                             // multigrid.cpp:165
     mgb200_solve_info info;
@@ -1002,8 +1025,15 @@ static int timestepper_common(double* uT, const double* u0, const double* v1, co
     }
     if (rc == MGB200_OK) rc = host ? mgb200_get_u_host(s, uT) : mgb200_get_u_device(s, uT, n + 1);   // :175
     if (last) *last = info;
-    mgb200_destroy(s);
+    if (rc != MGB200_OK) { mgb200_destroy(s); g_cached.s = nullptr; }
     return rc;
+}
+
+int mgb200_release_cached(void)
+{
+    std::lock_guard<std::mutex> lock(g_cached.mu);
+    if (g_cached.s) { mgb200_destroy(g_cached.s); g_cached.s = nullptr; }
+    return MGB200_OK;
 }
 
 int mgb200_timestepper_host(double* uT, const double* u0, const double* v1, const double* v2, double nu, int maxlvl,

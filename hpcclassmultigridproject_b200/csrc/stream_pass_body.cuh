@@ -517,7 +517,7 @@ inline Plan make_plan(long n, long nrows, int K, int sms, int force_swk = 0)
         const int nstrips = (int)((npairs + WK - 1) / WK);
         for (int nb = 1; nb <= 4096; nb = nb < 16 ? nb + 1 : nb * 2) {
             const long RB = (nrows + nb - 1) / nb;
-            if (nb > 1 && RB < 32) break;
+            if (nb > 1 && RB < 8) break;
             const int nbands = (int)((nrows + RB - 1) / RB);
             const long tiles = (long)nstrips * nbands;
             const long waves = (tiles + slots - 1) / slots;

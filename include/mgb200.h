@@ -223,6 +223,9 @@ int mgb200_timestepper_device(double *uT, const double *u0, const double *v1, co
                               double nu, int maxlvl, int n, double dt, double T, double dx,
                               double tol, int shape, const mgb200_options *opt,
                               mgb200_solve_info *last);
+/* The one-call drivers keep their last handle (the level towers in HBM) alive and reuse it when
+ * the next call has the same shape and parameters; this frees it. */
+int mgb200_release_cached(void);
 
 #ifdef __cplusplus
 }
