@@ -95,7 +95,8 @@ int mgb200_prolongation(double *fine, long ldf, const double *coarse, long ldc, 
 int mgb200_prolong_correct(double *u_fine, long ldf, const double *coarse, long ldc, long nc,
                            void *stream);
 
-/* c = a + b over the (n+1)^2 nodes (gscu.h:3 vecadd, gs.cu:7-11) */
+/* c = a + b over the (n+1)^2 nodes.  gscu.h:3 vecadd(x,y,z,len) computes x = y + z (gs.cu:7-11):
+ * it maps to mgb200_vecadd(x, y, z, ...) -- output first in both */
 int mgb200_vecadd(double *c, const double *a, const double *b, long n, long ld, void *stream);
 
 /* Initial conditions of the reference main (multigrid.cpp:206-233; NOT the buggy gs.cu:221-241):

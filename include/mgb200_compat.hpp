@@ -63,13 +63,14 @@ inline void prolongation(double* up, double* u, int n)
 inline void restriction(double* u, double* up, int n)
 { check(mgb200_restriction(u, n / 2 + 1L, up, n + 1L, n, nullptr), "restriction"); }
 
-// c = a + b over n entries (gscu.h:3).  n must be a whole field, (m+1)^2.
+// a = b + c over n entries (gscu.h:3, gs.cu:7-11: the FIRST argument is the output).  n must be a
+// whole field, (m+1)^2.
 inline void vecadd(double* a, double* b, double* c, long n)
 {
     long m = 0;
     while ((m + 1) * (m + 1) < n) ++m;
     if ((m + 1) * (m + 1) != n) throw std::runtime_error("vecadd: length is not a whole (m+1)^2 field");
-    check(mgb200_vecadd(c, a, b, m, m + 1, nullptr), "vecadd");
+    check(mgb200_vecadd(a, b, c, m, m + 1, nullptr), "vecadd");
 }
 
 // ---- drivers, reference argument lists (multigrid.cu:130-132: DEVICE pointers) --------------

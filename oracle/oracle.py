@@ -25,7 +25,8 @@ _dpp = C.POINTER(_dp)
 
 def build(quiet: bool = True) -> None:
     """Compile liboracle.so and, when /root/reference is mounted, oracle/_ref/*.so."""
-    subprocess.run(["make", "-C", HERE, "all"], check=True,
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.run(["make", "-C", HERE, "all"], check=True, env=env,
                    stdout=subprocess.DEVNULL if quiet else None,
                    stderr=subprocess.DEVNULL if quiet else None)
 
