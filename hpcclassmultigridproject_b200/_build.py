@@ -9,6 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgb200.so")
+TOOL = os.path.join(HERE, "multigrid_b200")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -40,6 +41,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.run(cmd, check=True, env=env)
+    # the command-line front end (tools/multigrid_b200.cpp): plain C++ over the C ABI
+    tool_src = os.path.join(HERE, "..", "tools", "multigrid_b200.cpp")
+    if os.path.exists(tool_src):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", TOOL, tool_src, "-L" + HERE, "-lmgb200", "-Wl,-rpath,$ORIGIN"],
+                       check=True, env=env)
     return LIB
 
 
