@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=N_FULL, help="finest grid N (default: the BASELINE config)")
     ap.add_argument("--plan", default="fused", choices=["fused", "unfused"])
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
