@@ -239,7 +239,7 @@ def run_own(args, rank, world):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and n == N_FULL and world == 1:
         try:
             traffic = json.load(open(tp)).get(f"{args.plan}_level0_bytes_per_launch")
         except Exception:

@@ -204,6 +204,11 @@ struct ThreadState {
     // bounds this kernel): the other-parity nodes of the current row become the next row's upper
     // neighbours, the nodes loaded from the row below become the next row's horizontal neighbours
     D2 c_up, c_mid;
+    // last stage of a POST_NORM2 pass: the residual of the nodes it has just updated costs no loads
+    // (all operands are in registers), so it accumulates their squares itself and the epilogue warps
+    // only visit the other colour.  nmask[par]: owned targets, nlo..nhi: owned interior rows
+    unsigned nmask[2];
+    int nlo, nhi;
     // producer: next row to store and next group to request, all advanced incrementally
     double* gst;        // global address of row `row`'s even run at the first owned pair
     unsigned nE8, nO8;  // bytes of the owned parts of the even / odd run
@@ -231,7 +236,7 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 {
     ThreadState s;
     const int warp = tid >> 5, lane = tid & 31;
-    s.acc = 0.0; s.c_up = D2{0.0, 0.0}; s.c_mid = D2{0.0, 0.0}; s.ok_cur = 0; s.okp[0] = s.okp[1] = 0; s.idx = 0; s.kk = 0; s.par = 0;
+    s.acc = 0.0; s.c_up = D2{0.0, 0.0}; s.c_mid = D2{0.0, 0.0}; s.nmask[0] = s.nmask[1] = 0; s.nlo = 1; s.nhi = 0; s.ok_cur = 0; s.okp[0] = s.okp[1] = 0; s.idx = 0; s.kk = 0; s.par = 0;
     s.lo = 1; s.hi = 0;                                  // empty range
     int off = 0;                                         // role row = t - off
     if (warp < NSTAGE) {
@@ -275,7 +280,13 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
         s.par = (s.idx + s.row) & 1;
         for (int e = 0; e < 2; ++e)
             for (int par = 0; par < 2; ++par)
-                if (target_ok(p, tl, s.kk + e, par)) s.okp[par] |= 1u << e;
+                if (target_ok(p, tl, s.kk + e, par)) {
+                    s.okp[par] |= 1u << e;
+                    if (s.kk + e >= HK && s.kk + e < HK + p.WK) s.nmask[par] |= 1u << e;      // owned pair
+                }
+        if (p.post == POST_NORM2 && p.K > 0 && s.idx == 2 * p.K - 1) {
+            s.nlo = tl.rb0 < 1 ? 1 : tl.rb0; s.nhi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1;
+        }
     }
     s.wphase = 0; s.wgroup = 0; s.wpar = 0;
     return s;
@@ -313,6 +324,12 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
     else {
         if (okb & 1u) sp_sts1(sm, c, o0);
         if (okb & 2u) sp_sts1(sm, c + 8u, o1);
+    }
+    if (st.row >= st.nlo && st.row <= st.nhi) {        // last stage of a norm pass: residual of the new values
+        const double r0 = Arith<ARITH>::residual(f.x, o0, up.x, n0, dn.x, n1, c0, p.st);
+        const double r1 = Arith<ARITH>::residual(f.y, o1, up.y, n1, dn.y, n2, c1, p.st);
+        if (st.nmask[PAR] & 1u) st.acc += r0 * r0;
+        if (st.nmask[PAR] & 2u) st.acc += r1 * r1;
     }
     st.c_up = m; st.c_mid = dn;
 }
@@ -365,6 +382,8 @@ SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
     const int q = st.row;
     if (q < st.lo || q > st.hi) return;
     if (p.post == POST_INJECT && (q & 1)) return;
+    // norm after smoothing: the last half-sweep's colour ((i+j) odd) is summed by the last stage itself
+    if (p.post == POST_NORM2 && p.K > 0 && ((q + PAR) & 1)) return;
     const unsigned po = PAR ? geo.swkb : 0u;
     const unsigned c = st.a_cur + po;                     // the node itself
     const unsigned o = st.a_cur + (geo.swkb - po);        // the other run at the same pair index
