@@ -110,26 +110,26 @@ __device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 0;" ::: 
 // The loops are unrolled by GROUP (= 4) steps so that the wait for the next TMA group sits at a
 // fixed place and, for the stage warps, the column parity of every step is a compile-time
 // constant: a step is a serial dependency chain and every branch in it is pure latency.
-template <int ARITH, int P0>
+template <int ARITH, int P0, bool NORM>
 __device__ __forceinline__ void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const bool feeds_store = (st.idx == 2 * p.K - 1);   // its rows go to the bulk-store engine: generic -> async proxy
     const int t1 = last_step(p, tl);
     int t = first_step(tl);
     for (; t + 3 <= t1; t += 4) {
-        stage_step<ARITH, P0>(p, geo, sm, st);
+        stage_step<ARITH, P0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
         step_barrier();
-        stage_step<ARITH, P0 ^ 1>(p, geo, sm, st);
+        stage_step<ARITH, P0 ^ 1, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
         step_barrier();
-        stage_step<ARITH, P0>(p, geo, sm, st);
+        stage_step<ARITH, P0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
         step_barrier();
-        stage_step<ARITH, P0 ^ 1>(p, geo, sm, st);
+        stage_step<ARITH, P0 ^ 1, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
         wait_group(tl, sm, st, t + 3);
@@ -137,7 +137,7 @@ __device__ __forceinline__ void stage_loop(const Params& p, const Tile& tl, cons
     }
     st.par = P0;
     for (; t <= t1; ++t) {
-        if (st.par) stage_step<ARITH, 1>(p, geo, sm, st); else stage_step<ARITH, 0>(p, geo, sm, st);
+        if (st.par) stage_step<ARITH, 1, NORM>(p, geo, sm, st); else stage_step<ARITH, 0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         stage_flip(st);
         end_step(tl, geo, sm, st, t);
@@ -163,8 +163,13 @@ template <int ARITH>
 __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int lane)
 {
     if (st.role == ROLE_STAGE) {
-        if (st.par) stage_loop<ARITH, 1>(p, tl, geo, sm, st);
-        else stage_loop<ARITH, 0>(p, tl, geo, sm, st);
+        if (st.nhi >= st.nlo) {          // last stage of a norm pass: also sums its own colour's residuals
+            if (st.par) stage_loop<ARITH, 1, true>(p, tl, geo, sm, st);
+            else stage_loop<ARITH, 0, true>(p, tl, geo, sm, st);
+        } else {
+            if (st.par) stage_loop<ARITH, 1, false>(p, tl, geo, sm, st);
+            else stage_loop<ARITH, 0, false>(p, tl, geo, sm, st);
+        }
     } else if (st.role == ROLE_PRE) {
         role_loop(p, tl, geo, sm, st, [&](int) { pre_step(p, tl, geo, sm, st); if (p.K == 0) sp_fence_async(); });
     } else if (st.role == ROLE_POST) {

@@ -300,7 +300,7 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 // With pair index kk even, the horizontal neighbours of targets (kk, kk+1) are three consecutive
 // nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd
 // columns: E[kk], E[kk+1], E[kk+2]).
-template <int ARITH, int PAR>
+template <int ARITH, int PAR, bool NORM = false>
 SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
@@ -325,7 +325,7 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
         if (okb & 1u) sp_sts1(sm, c, o0);
         if (okb & 2u) sp_sts1(sm, c + 8u, o1);
     }
-    if (st.row >= st.nlo && st.row <= st.nhi) {        // last stage of a norm pass: residual of the new values
+    if (NORM && st.row >= st.nlo && st.row <= st.nhi) {   // last stage of a norm pass: residual of the new values
         const double r0 = Arith<ARITH>::residual(f.x, o0, up.x, n0, dn.x, n1, c0, p.st);
         const double r1 = Arith<ARITH>::residual(f.y, o1, up.y, n1, dn.y, n2, c1, p.st);
         if (st.nmask[PAR] & 1u) st.acc += r0 * r0;
@@ -469,8 +469,13 @@ template <int ARITH>
 SP_FN void role_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int t, int lane)
 {
     if (st.role == ROLE_STAGE) {
-        if (st.par) stage_step<ARITH, 1>(p, geo, sm, st);
-        else stage_step<ARITH, 0>(p, geo, sm, st);
+        if (st.nhi >= st.nlo) {
+            if (st.par) stage_step<ARITH, 1, true>(p, geo, sm, st);
+            else stage_step<ARITH, 0, true>(p, geo, sm, st);
+        } else {
+            if (st.par) stage_step<ARITH, 1>(p, geo, sm, st);
+            else stage_step<ARITH, 0>(p, geo, sm, st);
+        }
         // the last stage's rows go to the bulk-store engine next step: generic -> async proxy
         if (st.idx == 2 * p.K - 1) sp_fence_async();
         stage_flip(st);
