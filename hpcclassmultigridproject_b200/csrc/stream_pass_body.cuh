@@ -43,6 +43,9 @@ constexpr int HK = 4;          // halo pairs per strip side (8 columns >= 2K+1 f
 constexpr int GROUP = 4;       // rows per TMA box
 constexpr int RING = 24;       // fine-row ring slots: rows t-4K-3 .. t in use + one group in flight
 constexpr int NGROUP = RING / GROUP;
+#ifndef MGB200_SP_PREFETCH
+#define MGB200_SP_PREFETCH 1
+#endif
 constexpr int LEAD = 5;        // a group is requested LEAD steps before its first row is consumed
 constexpr int CROWS = 3;       // coarse rows travelling with a group of fine rows
 constexpr int CW_MAX = SWK_MAX / 2 + 8;   // doubles per coarse parity run in smem
@@ -424,7 +427,7 @@ SP_FN void issue_group_loads(const Params& p, const Tile& tl, const Geo& geo, co
     if (p.pre)
         sp_tma_load(p, sm, FIELD_C, 4u * geo.ringb + (unsigned)gs * coarse, tl.k0 / 2, ((z + (int)p.row0) >> 1) - (int)p.crow0, gs);
     const int zp = z + 2 * GROUP;
-    if (zp + (int)p.row0 <= tl.R1) {
+    if (MGB200_SP_PREFETCH && zp + (int)p.row0 <= tl.R1) {
         if (!p.u_is_zero) sp_tma_prefetch(p, FIELD_U, tl.k0, zp);
         sp_tma_prefetch(p, FIELD_F, tl.k0, zp);
         sp_tma_prefetch(p, FIELD_V1, tl.k0, zp);
