@@ -20,6 +20,7 @@ struct Nccl {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -46,6 +47,7 @@ int load_nccl()
     BIND(Send, "ncclSend");
     BIND(Recv, "ncclRecv");
     BIND(AllReduce, "ncclAllReduce");
+    BIND(AllGather, "ncclAllGather");
     BIND(GroupStart, "ncclGroupStart");
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
@@ -123,6 +125,54 @@ int comm_allreduce_sum(Comm* c, double* buf, size_t count, cudaStream_t s)
 {
     if (!c || c->nranks == 1) return MGB200_OK;
     MGB_NCCL(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, c->nccl, s));
+    return MGB200_OK;
+}
+
+namespace {
+constexpr int PUSH_CTAS = 32, PUSH_TPB = 256;
+
+__global__ void __launch_bounds__(PUSH_TPB) k_peer_push(PeerPush a)
+{
+    const long tid = (long)blockIdx.x * PUSH_TPB + threadIdx.x, nth = (long)gridDim.x * PUSH_TPB;
+    for (int k = 0; k < a.nseg; ++k) {
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(a.seg[k].src);
+        double2* __restrict__ dst = reinterpret_cast<double2*>(a.seg[k].dst);
+        const long cnt = a.seg[k].count >> 1;
+        for (long i = tid; i < cnt; i += nth) dst[i] = src[i];
+    }
+    __threadfence_system();                       // this thread's peer stores before the arrival below
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned* arrive = reinterpret_cast<unsigned*>(a.sync + 16);
+    if (atomicInc(arrive, gridDim.x - 1) != gridDim.x - 1) return;   // wraps to 0 for the next launch
+    __threadfence_system();                       // every CTA's stores before the counters
+    for (int k = 0; k < a.nraise; ++k) atomicAdd_system(a.raise[k], 1);
+    for (int k = 0; k < a.nwait; ++k) {
+        const int slot = a.wait_slot[k];
+        const int want = a.sync[8 + slot] + a.wait_count[k];
+        int seen;
+        do {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.sync + slot) : "memory");
+        } while (seen - want < 0);
+        a.sync[8 + slot] = want;
+    }
+}
+}  // namespace
+
+int launch_peer_push(const PeerPush& a, cudaStream_t s)
+{
+    const bool copies = a.nseg > 0;
+    k_peer_push<<<copies ? PUSH_CTAS : 1, copies ? PUSH_TPB : 32, 0, s>>>(a);
+    return check_launch("k_peer_push");
+}
+
+int comm_allgather_bytes(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t s)
+{
+    if (!c || c->nranks == 1) {
+        MGB_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, s));
+        return MGB200_OK;
+    }
+    MGB_NCCL(g_nccl.AllGather(send, recv, bytes, ncclChar, c->nccl, s));
     return MGB200_OK;
 }
 

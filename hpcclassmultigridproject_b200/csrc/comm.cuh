@@ -21,5 +21,33 @@ struct P2P { int peer; double* buf; size_t count; bool send; };
 int comm_p2p(Comm* c, const P2P* ops, int nops, cudaStream_t s);
 // in-place sum of `count` doubles on every rank
 int comm_allreduce_sum(Comm* c, double* buf, size_t count, cudaStream_t s);
+// every rank contributes `bytes` bytes (device memory); recv holds nranks * bytes
+int comm_allgather_bytes(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t s);
+
+
+// ---- peer-memory transfers (NVLink stores + device-side counters, no NCCL on the path) ---------
+// One launch copies up to eight row blocks into other ranks' memory (mapped with CUDA IPC); its
+// last CTA then increments a counter on each destination rank and, if asked, waits until enough
+// increments have arrived in this rank's own counters.  Counter block of a rank (ints):
+//   [0..7]   arrivals, incremented by the peers       (slot 0: from rank-1, 1: from rank+1,
+//                                                      2: gather contributions, 3: scatter from rank 0)
+//   [8..15]  arrivals this rank has consumed so far
+//   [16]     CTA arrival counter of the running launch
+// Graph-replayable: every counter lives in device memory, nothing changes in the kernel arguments
+// between cycles.  Never run two ranks of one communicator on the same GPU (the waiter would spin
+// against a kernel that cannot be scheduled).
+constexpr int SYNC_FROM_UP = 0, SYNC_FROM_DOWN = 1, SYNC_GATHER = 2, SYNC_SCATTER = 3, SYNC_INTS = 32;
+struct PeerSeg { const double* src; double* dst; long count; };      // count doubles, multiple of 2, 16-byte aligned
+struct PeerPush {
+    PeerSeg seg[8];
+    int nseg;
+    int* raise[8];            // remote arrival counters to increment once the stores are out
+    int nraise;
+    int* sync;                // this rank's counter block
+    int wait_slot[2];         // own slots to wait on ...
+    int wait_count[2];        // ... for this many new arrivals each
+    int nwait;
+};
+int launch_peer_push(const PeerPush& a, cudaStream_t s);
 
 }  // namespace mgb200

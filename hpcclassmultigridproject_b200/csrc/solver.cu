@@ -133,6 +133,16 @@ struct mgb200_solver {
     int last_sharded = -1;             // index of the coarsest sharded level (-1: none)
     long shard_min_rows = 256;
     double* d_top[3] = {nullptr, nullptr, nullptr};   // dense rows 0..N/4+1 of u0,v1,v2 (tower input when sharded)
+    // peer-memory halo exchange: the slab neighbours' u twins and rhs of every sharded level and
+    // their counter blocks, mapped with CUDA IPC.  peer[0] = rank-1, peer[1] = rank+1.
+    struct PeerLevel { double* u[2] = {nullptr, nullptr}; double* rhs = nullptr; };
+    struct PeerRank { std::vector<PeerLevel> lv; int* sync = nullptr; };
+    bool p2p = false;
+    std::vector<PeerRank> peers;       // indexed by rank; only neighbours and rank 0 <-> everybody are mapped
+    int* d_sync = nullptr;             // this rank's counter block (layout: comm.cuh)
+    std::vector<void*> ipc_mapped;
+    int  setup_p2p();
+    double* d_flat_scratch() { return d_norm2 + 4; }   // a spare double for set-up collectives
     // MGB200_TRACE=1: CUDA events between the phases of a cycle, printed by rank 0 (diagnostics)
     bool tracing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -186,6 +196,10 @@ struct mgb200_solver {
 void mgb200_solver::release()
 {
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (stream) cudaStreamSynchronize(stream);
+    for (void* m : ipc_mapped) cudaIpcCloseMemHandle(m);     // the neighbours' memory first, then ours
+    ipc_mapped.clear();
+    p2p = false;
     for (auto& g : lv) {
         cudaFree(g.u[0]); cudaFree(g.u[1]); cudaFree(g.rhs); cudaFree(g.v1); cudaFree(g.v2);
     }
@@ -195,6 +209,7 @@ void mgb200_solver::release()
     cudaFree(d_coarse_iters); d_coarse_iters = nullptr;
     cudaFree(d_flat[0]); cudaFree(d_flat[1]); d_flat[0] = d_flat[1] = nullptr;
     for (auto& t : d_top) { cudaFree(t); t = nullptr; }
+    cudaFree(d_sync); d_sync = nullptr;
     if (comm) { comm_destroy(comm); comm = nullptr; }
     if (h_norm2) { cudaFreeHost(h_norm2); h_norm2 = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
@@ -242,6 +257,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
     MGB_CUDA(cudaMalloc(&d_coarse_iters, sizeof(int)));
     MGB_CUDA(cudaMallocHost(&h_norm2, 8 * sizeof(double)));
     MGB_CUDA(cudaStreamSynchronize(stream));
+    if (P > 1) MGB_TRY(setup_p2p());
     return MGB200_OK;
 }
 
@@ -307,11 +323,124 @@ void mgb200_solver::fill_pass_window(StreamPassArgs& a, const Level& g, const Le
     a.crow0 = c.mem_lo; a.crows_mem = c.rows_mem();
 }
 
+// Map the other ranks' arrays into this process (CUDA IPC over NVLink peer access): the slab
+// neighbours' u twins / rhs of every sharded level, and for the agglomeration step rank 0's coarse
+// rhs (on every rank) and every rank's coarse u (on rank 0).  All ranks agree on the outcome: if
+// any mapping fails, everybody falls back to NCCL send/receive.
+int mgb200_solver::setup_p2p()
+{
+    p2p = false;
+    const char* e = getenv("MGB200_P2P");
+    const bool want = !(e && atoi(e) == 0) && P <= 8;
+    const int nl = last_sharded + 1;               // sharded levels 0..nl-1, level nl is the first agglomerated one
+    const int nh = 3 * (nl + 1) + 1;               // u[0], u[1], rhs per level, then the counter block
+    MGB_CUDA(cudaMalloc(&d_sync, SYNC_INTS * sizeof(int)));
+    MGB_CUDA(cudaMemsetAsync(d_sync, 0, SYNC_INTS * sizeof(int), stream));
+    std::vector<cudaIpcMemHandle_t> mine(nh), all((size_t)nh * P);
+    bool ok = want;
+    for (int l = 0; l <= nl && ok; ++l) {
+        ok = ok && cudaIpcGetMemHandle(&mine[3 * l + 0], lv[l].u[0]) == cudaSuccess;
+        ok = ok && cudaIpcGetMemHandle(&mine[3 * l + 1], lv[l].u[1]) == cudaSuccess;
+        ok = ok && cudaIpcGetMemHandle(&mine[3 * l + 2], lv[l].rhs) == cudaSuccess;
+    }
+    ok = ok && cudaIpcGetMemHandle(&mine[3 * (nl + 1)], d_sync) == cudaSuccess;
+    cudaGetLastError();
+    // handles travel through one byte all-gather (collective: every rank takes part, ok or not)
+    void *d_send = nullptr, *d_recv = nullptr;
+    const size_t hb = (size_t)nh * sizeof(cudaIpcMemHandle_t);
+    MGB_CUDA(cudaMalloc(&d_send, hb));
+    MGB_CUDA(cudaMalloc(&d_recv, hb * P));
+    MGB_CUDA(cudaMemcpyAsync(d_send, mine.data(), hb, cudaMemcpyHostToDevice, stream));
+    MGB_TRY(comm_allgather_bytes(comm, d_send, d_recv, hb, stream));
+    MGB_CUDA(cudaMemcpyAsync(all.data(), d_recv, hb * P, cudaMemcpyDeviceToHost, stream));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_send); cudaFree(d_recv);
+    peers.assign(P, PeerRank{});
+    auto open = [&](int r, int idx) -> void* {
+        void* ptr = nullptr;
+        if (!ok) return nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r * nh + idx], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); ok = false; return nullptr;
+        }
+        ipc_mapped.push_back(ptr);
+        return ptr;
+    };
+    for (int r = 0; r < P; ++r) {
+        if (r == rank) continue;
+        const bool neighbour = r == rank - 1 || r == rank + 1;
+        const bool agglo = rank == 0 || r == 0;          // rank 0 <-> everybody
+        if (!neighbour && !agglo) continue;
+        PeerRank& pr = peers[r];
+        pr.lv.assign(nl + 1, PeerLevel{});
+        if (neighbour)
+            for (int l = 0; l < nl; ++l) {
+                pr.lv[l].u[0] = (double*)open(r, 3 * l + 0);
+                pr.lv[l].u[1] = (double*)open(r, 3 * l + 1);
+                pr.lv[l].rhs = (double*)open(r, 3 * l + 2);
+            }
+        if (rank == 0) { pr.lv[nl].u[0] = (double*)open(r, 3 * nl + 0); pr.lv[nl].u[1] = (double*)open(r, 3 * nl + 1); }
+        if (r == 0) pr.lv[nl].rhs = (double*)open(r, 3 * nl + 2);
+        pr.sync = (int*)open(r, 3 * (nl + 1));
+    }
+    // unanimous or not at all
+    double flag = ok ? 1.0 : 0.0;
+    MGB_CUDA(cudaMemcpyAsync(d_flat_scratch(), &flag, sizeof(double), cudaMemcpyHostToDevice, stream));
+    MGB_TRY(comm_allreduce_sum(comm, d_flat_scratch(), 1, stream));
+    MGB_CUDA(cudaMemcpyAsync(&flag, d_flat_scratch(), sizeof(double), cudaMemcpyDeviceToHost, stream));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    p2p = flag > P - 0.5;
+    if (!p2p) {
+        for (void* m : ipc_mapped) cudaIpcCloseMemHandle(m);
+        ipc_mapped.clear();
+        peers.clear();
+    }
+    if (getenv("MGB200_TRACE") && rank == 0) fprintf(stderr, "MGB200_TRACE halo transport: %s\n", p2p ? "peer memory" : "nccl send/recv");
+    return MGB200_OK;
+}
+
 // Slab neighbours swap SLAB_HALO boundary rows of array `a` of level g (and optionally of a second
-// array of another sharded level) in one NCCL group.  Rows are contiguous: no packing.
+// array of another sharded level).  Rows are contiguous: no packing.  Peer-memory transport: one
+// kernel stores the rows straight into the neighbours' halo rows and synchronises through
+// device-side counters (see comm.cuh); otherwise one NCCL send/receive group.
+//
+// Why a neighbour may write into our halo rows while we are still computing: consecutive
+// exchanges target different arrays (the u twins alternate, rhs belongs to the child level), a
+// pass never reads the halo rows of the array it produces, and a rank cannot run more than one
+// exchange ahead of its neighbour because it has to wait for that neighbour's counter.
 int mgb200_solver::exchange_halo(Level& g, double* a, Level* g2, double* a2)
 {
     if (P == 1) return MGB200_OK;
+    if (p2p) {
+        PeerPush pp{};
+        pp.sync = d_sync;
+        if (rank > 0) {         // we are rank-1's lower neighbour
+            pp.raise[pp.nraise++] = peers[rank - 1].sync + SYNC_FROM_DOWN;
+            pp.wait_slot[pp.nwait] = SYNC_FROM_UP; pp.wait_count[pp.nwait++] = 1;
+        }
+        if (rank < P - 1) {     // and rank+1's upper neighbour
+            pp.raise[pp.nraise++] = peers[rank + 1].sync + SYNC_FROM_UP;
+            pp.wait_slot[pp.nwait] = SYNC_FROM_DOWN; pp.wait_count[pp.nwait++] = 1;
+        }
+        Level* lvls[2] = {&g, g2};
+        double* arrs[2] = {a, a2};
+        for (int k = 0; k < 2; ++k) {
+            Level* q = lvls[k];
+            if (!q || !q->sharded) continue;
+            const int l = (int)(q - lv.data());
+            const long cnt = SLAB_HALO * q->L.pitch;
+            for (int d = 0; d < 2; ++d) {
+                const int nb = d == 0 ? rank - 1 : rank + 1;
+                if (nb < 0 || nb >= P) continue;
+                const PeerLevel& pl = peers[nb].lv[l];
+                double* pbase = arrs[k] == q->u[0] ? pl.u[0] : arrs[k] == q->u[1] ? pl.u[1] : arrs[k] == q->rhs ? pl.rhs : nullptr;
+                if (!pbase) return fail(MGB200_ERR_INVALID, "exchange_halo: array is not shared with the neighbours");
+                const Slab w = slab_of(q->n, P, nb);
+                const long row = d == 0 ? q->own_lo : q->own_hi - SLAB_HALO + 1;   // our first / last owned rows
+                pp.seg[pp.nseg++] = PeerSeg{arrs[k] + (row - q->mem_lo) * q->L.pitch, pbase + (row - w.mem_lo) * q->L.pitch, cnt};
+            }
+        }
+        return launch_peer_push(pp, stream);
+    }
     P2P ops[8];
     int n = 0;
     Level* lvls[2] = {&g, g2};
@@ -339,6 +468,25 @@ int mgb200_solver::gather_to_root(Level& c, double* arr)
 {
     if (P == 1) return MGB200_OK;
     const long nf = lv[last_sharded].n;
+    if (p2p) {
+        // every other rank stores its rows into rank 0's array; rank 0 waits for P-1 arrivals.
+        // (Rank 0 last read this array in the previous cycle, which every rank has left behind:
+        // nobody starts a cycle before the scatter of the one before.)
+        PeerPush pp{};
+        pp.sync = d_sync;
+        if (rank == 0) {
+            pp.wait_slot[0] = SYNC_GATHER; pp.wait_count[0] = P - 1; pp.nwait = 1;
+        } else {
+            if (arr != c.rhs) return fail(MGB200_ERR_INVALID, "gather_to_root: only the coarse rhs is shared with rank 0");
+            const int lc = (int)(&c - lv.data());
+            const Slab w0 = Slab{0, c.n, 0, c.n};
+            pp.seg[0] = PeerSeg{arr + (c.own_lo - c.mem_lo) * c.L.pitch, peers[0].lv[lc].rhs + (c.own_lo - w0.mem_lo) * c.L.pitch,
+                                (c.own_hi - c.own_lo + 1) * c.L.pitch};
+            pp.nseg = 1;
+            pp.raise[0] = peers[0].sync + SYNC_GATHER; pp.nraise = 1;
+        }
+        return launch_peer_push(pp, stream);
+    }
     std::vector<P2P> ops;
     if (rank == 0) {
         for (int r = 1; r < P; ++r) {
@@ -356,6 +504,27 @@ int mgb200_solver::scatter_from_root(Level& c, double* arr)
 {
     if (P == 1) return MGB200_OK;
     const long nf = lv[last_sharded].n;
+    if (p2p) {
+        // rank 0 stores every rank's window into that rank's array, the others wait for it.  The
+        // twin index is the same on every rank: a level's passes come in pairs (down + up), and
+        // the ranks that do not run the coarse levels never flip theirs.
+        PeerPush pp{};
+        pp.sync = d_sync;
+        const int lc = (int)(&c - lv.data());
+        const int twin = arr == c.u[0] ? 0 : arr == c.u[1] ? 1 : -1;
+        if (twin != 0) return fail(MGB200_ERR_STATE, "scatter_from_root: coarse iterate is not in twin 0");
+        if (rank == 0) {
+            for (int r = 1; r < P; ++r) {
+                const Slab w = child_slab_of(nf, P, r);
+                pp.seg[pp.nseg++] = PeerSeg{arr + (w.mem_lo - c.mem_lo) * c.L.pitch, peers[r].lv[lc].u[twin],
+                                            (w.mem_hi - w.mem_lo + 1) * c.L.pitch};
+                pp.raise[pp.nraise++] = peers[r].sync + SYNC_SCATTER;
+            }
+        } else {
+            pp.wait_slot[0] = SYNC_SCATTER; pp.wait_count[0] = 1; pp.nwait = 1;
+        }
+        return launch_peer_push(pp, stream);
+    }
     std::vector<P2P> ops;
     if (rank == 0) {
         for (int r = 1; r < P; ++r) {
