@@ -159,6 +159,44 @@ __global__ void __launch_bounds__(PUSH_TPB) k_peer_push(PeerPush a)
 }
 }  // namespace
 
+namespace {
+__device__ __forceinline__ void wait_arrivals(int* sync, int slot, int count)
+{
+    const int want = sync[8 + slot] + count;
+    int seen;
+    do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sync + slot) : "memory");
+    } while (seen - want < 0);
+    sync[8 + slot] = want;
+}
+
+__global__ void k_norm_allreduce(NormReduce a)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (a.rank != 0) {
+        *reinterpret_cast<volatile double*>(a.peer_red[0] + a.rank) = a.value[0];
+        __threadfence_system();
+        atomicAdd_system(a.peer_sync[0] + SYNC_NORM_UP, 1);
+        wait_arrivals(a.sync, SYNC_NORM_DOWN, 1);
+        a.value[0] = *reinterpret_cast<volatile double*>(a.red);
+    } else {
+        wait_arrivals(a.sync, SYNC_NORM_UP, a.nranks - 1);
+        double sum = a.value[0];
+        for (int r = 1; r < a.nranks; ++r) sum = __dadd_rn(sum, *reinterpret_cast<volatile double*>(a.red + r));
+        a.value[0] = sum;
+        for (int r = 1; r < a.nranks; ++r) *reinterpret_cast<volatile double*>(a.peer_red[r]) = sum;
+        __threadfence_system();
+        for (int r = 1; r < a.nranks; ++r) atomicAdd_system(a.peer_sync[r] + SYNC_NORM_DOWN, 1);
+    }
+}
+}  // namespace
+
+int launch_norm_allreduce(const NormReduce& a, cudaStream_t s)
+{
+    k_norm_allreduce<<<1, 32, 0, s>>>(a);
+    return check_launch("k_norm_allreduce");
+}
+
 int launch_peer_push(const PeerPush& a, cudaStream_t s)
 {
     const bool copies = a.nseg > 0;

@@ -30,13 +30,15 @@ int comm_allgather_bytes(Comm* c, const void* send, void* recv, size_t bytes, cu
 // last CTA then increments a counter on each destination rank and, if asked, waits until enough
 // increments have arrived in this rank's own counters.  Counter block of a rank (ints):
 //   [0..7]   arrivals, incremented by the peers       (slot 0: from rank-1, 1: from rank+1,
-//                                                      2: gather contributions, 3: scatter from rank 0)
+//                                                      2: gather contributions, 3: scatter from rank 0,
+//                                                      4: norm contributions, 5: norm result from rank 0)
 //   [8..15]  arrivals this rank has consumed so far
 //   [16]     CTA arrival counter of the running launch
 // Graph-replayable: every counter lives in device memory, nothing changes in the kernel arguments
 // between cycles.  Never run two ranks of one communicator on the same GPU (the waiter would spin
 // against a kernel that cannot be scheduled).
-constexpr int SYNC_FROM_UP = 0, SYNC_FROM_DOWN = 1, SYNC_GATHER = 2, SYNC_SCATTER = 3, SYNC_INTS = 32;
+constexpr int SYNC_FROM_UP = 0, SYNC_FROM_DOWN = 1, SYNC_GATHER = 2, SYNC_SCATTER = 3, SYNC_NORM_UP = 4, SYNC_NORM_DOWN = 5,
+              SYNC_INTS = 32;
 struct PeerSeg { const double* src; double* dst; long count; };      // count doubles, multiple of 2, 16-byte aligned
 struct PeerPush {
     PeerSeg seg[8];
@@ -49,5 +51,19 @@ struct PeerPush {
     int nwait;
 };
 int launch_peer_push(const PeerPush& a, cudaStream_t s);
+
+// Sum of one double per rank through rank 0, in rank order (deterministic, identical on every
+// rank): the others store their term into rank 0's `red[rank]`, rank 0 adds them up and stores
+// the total into everybody's `red[0]`.  One single-thread launch per rank.
+constexpr int RED_DOUBLES = 16;
+struct NormReduce {
+    double* value;            // in: this rank's term, out: the total
+    double* red;              // this rank's landing block (RED_DOUBLES doubles, IPC-shared)
+    double* peer_red[8];      // rank 0: red of rank r at [r]; other ranks: rank 0's red at [0]
+    int* sync;                // this rank's counter block
+    int* peer_sync[8];        // same indexing as peer_red
+    int rank, nranks;
+};
+int launch_norm_allreduce(const NormReduce& a, cudaStream_t s);
 
 }  // namespace mgb200

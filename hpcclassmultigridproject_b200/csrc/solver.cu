@@ -104,6 +104,30 @@ static Slab child_slab_of(long n_fine, int P, int rank)
     return w;
 }
 
+// mg_outer's loop state (multigrid.cpp:100-116) when the loop itself runs on the device
+struct LoopState {
+    double res0, tol;
+    int iter, max_cycle;
+    double hist[52];
+};
+
+// while (iter < max_cycle && res/res0 > tol) -- the test before the first cycle (res == res0)
+__global__ void k_loop_begin(cudaGraphConditionalHandle h, const double* norm2, LoopState* st, double tol, int max_cycle)
+{
+    const double r0 = sqrt(norm2[0]);                                             // gs.cpp:106
+    st->res0 = r0; st->tol = tol; st->iter = 0; st->max_cycle = max_cycle; st->hist[0] = r0;
+    cudaGraphSetConditional(h, (0 < max_cycle && r0 / r0 > tol) ? 1u : 0u);
+}
+
+// ... and after every cycle
+__global__ void k_loop_check(cudaGraphConditionalHandle h, const double* norm2, LoopState* st)
+{
+    const double r = sqrt(norm2[0]);
+    const int it = ++st->iter;
+    st->hist[it] = r;
+    cudaGraphSetConditional(h, (it < st->max_cycle && r / st->res0 > st->tol) ? 1u : 0u);
+}
+
 }  // namespace mgb200
 
 using namespace mgb200;
@@ -124,8 +148,18 @@ struct mgb200_solver {
     double* d_flat[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec = nullptr;
     long graph_kernels = 0;
+    // the whole mg_outer loop as one graph: a WHILE node around the cycle, condition set on the device
+    cudaGraphExec_t loop_exec = nullptr;
+    bool loop_failed = false;
+    long loop_kernels = 0;             // kernels of one trip through the loop body
+    LoopState* d_loop = nullptr;
+    LoopState* h_loop = nullptr;       // pinned
+    int  build_loop_graph();
+    bool device_loop() const { return opt.use_graph && !loop_failed && (P == 1 || p2p); }
     long launches = 0;
     bool have_fields = false, have_rhs = false;
+    bool norm_is_res0 = false;         // d_norm2[0] holds ||r0||^2 of the current right-hand side (no cycle since form_rhs)
+    bool res0_on_host = false;         // ... and `res0` has been read back
     double res0 = 0, res = 0;
     // row-slab sharding (one process per GPU)
     Comm* comm = nullptr;
@@ -136,10 +170,12 @@ struct mgb200_solver {
     // peer-memory halo exchange: the slab neighbours' u twins and rhs of every sharded level and
     // their counter blocks, mapped with CUDA IPC.  peer[0] = rank-1, peer[1] = rank+1.
     struct PeerLevel { double* u[2] = {nullptr, nullptr}; double* rhs = nullptr; };
-    struct PeerRank { std::vector<PeerLevel> lv; int* sync = nullptr; };
+    struct PeerRank { std::vector<PeerLevel> lv; int* sync = nullptr; double* red = nullptr; };
     bool p2p = false;
     std::vector<PeerRank> peers;       // indexed by rank; only neighbours and rank 0 <-> everybody are mapped
     int* d_sync = nullptr;             // this rank's counter block (layout: comm.cuh)
+    double* d_red = nullptr;           // landing block of the norm reduction through rank 0
+    int  allreduce_norm();             // d_norm2[0] <- sum over ranks
     std::vector<void*> ipc_mapped;
     int  setup_p2p();
     double* d_flat_scratch() { return d_norm2 + 4; }   // a spare double for set-up collectives
@@ -180,7 +216,7 @@ struct mgb200_solver {
     int  record_cycle();               // cycle_body(0) + convergence norm, on `stream`
     int  run_cycle_async();
     int  read_norm(double* out);
-    int  form_rhs(double* res0_out);
+    int  form_rhs(double* res0_out, bool sync = true);
     int  solve(mgb200_solve_info* info);
     int  get_u_natural(double* dst_dev, long ld);
     int  alloc_levels();
@@ -196,6 +232,9 @@ struct mgb200_solver {
 void mgb200_solver::release()
 {
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (loop_exec) { cudaGraphExecDestroy(loop_exec); loop_exec = nullptr; }
+    cudaFree(d_loop); d_loop = nullptr;
+    if (h_loop) { cudaFreeHost(h_loop); h_loop = nullptr; }
     if (stream) cudaStreamSynchronize(stream);
     for (void* m : ipc_mapped) cudaIpcCloseMemHandle(m);     // the neighbours' memory first, then ours
     ipc_mapped.clear();
@@ -210,6 +249,7 @@ void mgb200_solver::release()
     cudaFree(d_flat[0]); cudaFree(d_flat[1]); d_flat[0] = d_flat[1] = nullptr;
     for (auto& t : d_top) { cudaFree(t); t = nullptr; }
     cudaFree(d_sync); d_sync = nullptr;
+    cudaFree(d_red); d_red = nullptr;
     if (comm) { comm_destroy(comm); comm = nullptr; }
     if (h_norm2) { cudaFreeHost(h_norm2); h_norm2 = nullptr; }
     if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
@@ -235,6 +275,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
     // single-GPU one; MGB200_SHARDED_GRAPH=0 issues everything directly on the stream instead
     if (P > 1) { const char* e = getenv("MGB200_SHARDED_GRAPH"); if (e && atoi(e) == 0) opt.use_graph = 0; }
     if (getenv("MGB200_TRACE")) { tracing = true; opt.use_graph = 0; }
+    { const char* e = getenv("MGB200_DEVICE_LOOP"); if (e && atoi(e) == 0) loop_failed = true; }   // host-side mg_outer loop
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MGB200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
@@ -256,6 +297,9 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
     MGB_CUDA(cudaMemsetAsync(d_norm2, 0, 8 * sizeof(double), stream));
     MGB_CUDA(cudaMalloc(&d_coarse_iters, sizeof(int)));
     MGB_CUDA(cudaMallocHost(&h_norm2, 8 * sizeof(double)));
+    MGB_CUDA(cudaMalloc(&d_loop, sizeof(LoopState)));
+    MGB_CUDA(cudaMemsetAsync(d_loop, 0, sizeof(LoopState), stream));
+    MGB_CUDA(cudaMallocHost(&h_loop, sizeof(LoopState)));
     MGB_CUDA(cudaStreamSynchronize(stream));
     if (P > 1) MGB_TRY(setup_p2p());
     return MGB200_OK;
@@ -333,9 +377,11 @@ int mgb200_solver::setup_p2p()
     const char* e = getenv("MGB200_P2P");
     const bool want = !(e && atoi(e) == 0) && P <= 8;
     const int nl = last_sharded + 1;               // sharded levels 0..nl-1, level nl is the first agglomerated one
-    const int nh = 3 * (nl + 1) + 1;               // u[0], u[1], rhs per level, then the counter block
+    const int nh = 3 * (nl + 1) + 2;               // u[0], u[1], rhs per level, then the counter and reduction blocks
     MGB_CUDA(cudaMalloc(&d_sync, SYNC_INTS * sizeof(int)));
     MGB_CUDA(cudaMemsetAsync(d_sync, 0, SYNC_INTS * sizeof(int), stream));
+    MGB_CUDA(cudaMalloc(&d_red, RED_DOUBLES * sizeof(double)));
+    MGB_CUDA(cudaMemsetAsync(d_red, 0, RED_DOUBLES * sizeof(double), stream));
     std::vector<cudaIpcMemHandle_t> mine(nh), all((size_t)nh * P);
     bool ok = want;
     for (int l = 0; l <= nl && ok; ++l) {
@@ -344,6 +390,7 @@ int mgb200_solver::setup_p2p()
         ok = ok && cudaIpcGetMemHandle(&mine[3 * l + 2], lv[l].rhs) == cudaSuccess;
     }
     ok = ok && cudaIpcGetMemHandle(&mine[3 * (nl + 1)], d_sync) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine[3 * (nl + 1) + 1], d_red) == cudaSuccess;
     cudaGetLastError();
     // handles travel through one byte all-gather (collective: every rank takes part, ok or not)
     void *d_send = nullptr, *d_recv = nullptr;
@@ -381,6 +428,7 @@ int mgb200_solver::setup_p2p()
         if (rank == 0) { pr.lv[nl].u[0] = (double*)open(r, 3 * nl + 0); pr.lv[nl].u[1] = (double*)open(r, 3 * nl + 1); }
         if (r == 0) pr.lv[nl].rhs = (double*)open(r, 3 * nl + 2);
         pr.sync = (int*)open(r, 3 * (nl + 1));
+        if (agglo) pr.red = (double*)open(r, 3 * (nl + 1) + 1);
     }
     // unanimous or not at all
     double flag = ok ? 1.0 : 0.0;
@@ -396,6 +444,18 @@ int mgb200_solver::setup_p2p()
     }
     if (getenv("MGB200_TRACE") && rank == 0) fprintf(stderr, "MGB200_TRACE halo transport: %s\n", p2p ? "peer memory" : "nccl send/recv");
     return MGB200_OK;
+}
+
+// d_norm2[0] <- sum over ranks: through rank 0 over peer memory, or NCCL all-reduce
+int mgb200_solver::allreduce_norm()
+{
+    if (P == 1) return MGB200_OK;
+    if (!p2p) return comm_allreduce_sum(comm, d_norm2, 1, stream);
+    NormReduce a{};
+    a.value = d_norm2; a.red = d_red; a.sync = d_sync; a.rank = rank; a.nranks = P;
+    if (rank == 0) for (int r = 1; r < P; ++r) { a.peer_red[r] = peers[r].red; a.peer_sync[r] = peers[r].sync; }
+    else { a.peer_red[0] = peers[0].red; a.peer_sync[0] = peers[0].sync; }
+    return launch_norm_allreduce(a, stream);
 }
 
 // Slab neighbours swap SLAB_HALO boundary rows of array `a` of level g (and optionally of a second
@@ -686,7 +746,7 @@ int mgb200_solver::record_cycle()
         // the level-0 up leg already produced the per-tile sums of squares (its LAST chunk did)
         const int last_k = opt.niter == 0 ? 0 : ((opt.niter - 1) % 3) + 1;
         MGB_TRY(launch_reduce_partials(d_partials, stream_pass_tiles(N, lv[0].own_hi - lv[0].own_lo + 1, last_k), d_norm2, stream));
-        MGB_TRY(comm_allreduce_sum(comm, d_norm2, 1, stream));
+        MGB_TRY(allreduce_norm());
         mark("norm");
     } else {
         MGB_TRY(residual_norm_level0());
@@ -697,6 +757,8 @@ int mgb200_solver::record_cycle()
 int mgb200_solver::run_cycle_async()
 {
     if (!have_rhs) return fail(MGB200_ERR_STATE, "cycle before form_rhs");
+    if (!res0_on_host && norm_is_res0) { MGB_TRY(read_norm(&res0)); res0_on_host = true; }
+    norm_is_res0 = false;
     if (!opt.use_graph) {
         const long before = launch_counter();
         MGB_TRY(record_cycle());
@@ -729,6 +791,56 @@ int mgb200_solver::run_cycle_async()
     return MGB200_OK;
 }
 
+// mg_outer as ONE graph: [k_loop_begin] -> WHILE { cycle ; k_loop_check }.  The host launches it
+// once per time step and reads the loop state afterwards; no round trip per cycle.
+int mgb200_solver::build_loop_graph()
+{
+    std::vector<int> cur0;
+    for (auto& g : lv) cur0.push_back(g.cur);
+    cudaGraph_t graph = nullptr;
+    auto bail = [&](const char* what, cudaError_t e) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        loop_failed = true;
+        return fail(MGB200_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    cudaError_t e = cudaGraphCreate(&graph, 0);
+    if (e != cudaSuccess) return bail("cudaGraphCreate", e);
+    cudaGraphConditionalHandle h;
+    e = cudaGraphConditionalHandleCreate(&h, graph, 0, 0);
+    if (e != cudaSuccess) return bail("cudaGraphConditionalHandleCreate", e);
+    cudaKernelNodeParams kp{};
+    double tol_ = tol; int maxc = opt.max_cycle;
+    void* args[] = {&h, &d_norm2, &d_loop, &tol_, &maxc};
+    kp.func = (void*)k_loop_begin; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+    cudaGraphNode_t n_begin, n_while;
+    e = cudaGraphAddKernelNode(&n_begin, graph, nullptr, 0, &kp);
+    if (e != cudaSuccess) return bail("cudaGraphAddKernelNode", e);
+    cudaGraphNodeParams cp{};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = h; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+    e = cudaGraphAddNode(&n_while, graph, &n_begin, 1, &cp);
+    if (e != cudaSuccess) return bail("cudaGraphAddNode(conditional)", e);
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    const long before = launch_counter();
+    e = cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return bail("cudaStreamBeginCaptureToGraph", e);
+    int rc = record_cycle();
+    if (rc == MGB200_OK) { k_loop_check<<<1, 1, 0, stream>>>(h, d_norm2, d_loop); rc = check_launch("k_loop_check"); }
+    cudaGraph_t captured = nullptr;
+    e = cudaStreamEndCapture(stream, &captured);
+    loop_kernels = launch_counter() - before;
+    launch_counter() = before;          // captured, not launched
+    if (rc != MGB200_OK) { cudaGraphDestroy(graph); loop_failed = true; return rc; }
+    if (e != cudaSuccess) return bail("cudaStreamEndCapture(loop body)", e);
+    for (size_t l = 0; l < lv.size(); ++l)
+        if (lv[l].cur != cur0[l]) { cudaGraphDestroy(graph); loop_failed = true; return fail(MGB200_ERR_STATE, "cycle does not restore buffer parity"); }
+    e = cudaGraphInstantiate(&loop_exec, graph, 0);
+    if (e != cudaSuccess) { loop_exec = nullptr; return bail("cudaGraphInstantiate(loop)", e); }
+    cudaGraphDestroy(graph);
+    return MGB200_OK;
+}
+
 int mgb200_solver::read_norm(double* out)
 {
     MGB_CUDA(cudaMemcpyAsync(h_norm2, d_norm2, sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -739,7 +851,7 @@ int mgb200_solver::read_norm(double* out)
 }
 
 // compute_rhs (multigrid.cpp:167) fused with the initial residual norm (multigrid.cpp:104-105)
-int mgb200_solver::form_rhs(double* res0_out)
+int mgb200_solver::form_rhs(double* res0_out, bool sync)
 {
     if (!have_fields) return fail(MGB200_ERR_STATE, "form_rhs before set_fields");
     Level& g = lv[0];
@@ -751,12 +863,15 @@ int mgb200_solver::form_rhs(double* res0_out)
         const long ilo = g.own_lo < 1 ? 1 : g.own_lo, ihi = g.own_hi > g.n - 1 ? g.n - 1 : g.own_hi;
         MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream, ilo, ihi));
         MGB_TRY(launch_reduce_partials(d_partials, rows_partials_count(g.n, ihi - ilo + 1), d_norm2, stream));
-        MGB_TRY(comm_allreduce_sum(comm, d_norm2, 1, stream));
+        MGB_TRY(allreduce_norm());
         MGB_TRY(exchange_halo(g, g.rhs));
     }
     count(before);
     have_rhs = true;
+    norm_is_res0 = true; res0_on_host = false;
+    if (!sync) return MGB200_OK;       // the device-side loop takes res0 from d_norm2 itself
     MGB_TRY(read_norm(&res0));
+    res0_on_host = true;
     if (res0_out) *res0_out = res0;
     return MGB200_OK;
 }
@@ -765,6 +880,34 @@ int mgb200_solver::form_rhs(double* res0_out)
 int mgb200_solver::solve(mgb200_solve_info* info)
 {
     if (!have_rhs) return fail(MGB200_ERR_STATE, "solve before form_rhs");
+    if (device_loop() && norm_is_res0 && !loop_exec) {
+        // every rank takes the same decision: the capture works everywhere or nowhere
+        if (build_loop_graph() != MGB200_OK) {
+            fprintf(stderr, "mgb200: device-side solve loop unavailable (%s); using the host loop\n", mgb200_last_error());
+            if (P > 1) return MGB200_ERR_CUDA;
+        }
+    }
+    if (device_loop() && norm_is_res0 && loop_exec) {
+        // d_norm2[0] still holds ||r0||^2 from form_rhs (multigrid.cpp:104-105)
+        MGB_CUDA(cudaGraphLaunch(loop_exec, stream));
+        MGB_CUDA(cudaMemcpyAsync(h_loop, d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, stream));
+        MGB_CUDA(cudaStreamSynchronize(stream));
+        norm_is_res0 = false; res0_on_host = true;
+        const int it = h_loop->iter;
+        launches += 1 + (long)it * loop_kernels;
+        res0 = h_loop->res0; res = h_loop->hist[it];
+        if (info) {
+            std::memset(info, 0, sizeof(*info));
+            for (int k = 0; k <= it; ++k) info->hist[k] = h_loop->hist[k];
+            info->cycles = it; info->res0 = res0; info->res = res; info->converged = (res / res0 <= tol) ? 1 : 0;
+        }
+        return MGB200_OK;
+    }
+    if (!res0_on_host) {
+        if (!norm_is_res0) return fail(MGB200_ERR_STATE, "solve: initial residual norm unknown; call form_rhs first");
+        MGB_TRY(read_norm(&res0));
+        res0_on_host = true;
+    }
     double r0 = res0, r = res0;
     int it = 0;
     if (info) { std::memset(info, 0, sizeof(*info)); info->hist[0] = r0; }
@@ -1010,7 +1153,7 @@ int mgb200_timestep(mgb200_solver* s, int nsteps, mgb200_solve_info* infos)
 {
     if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
     for (int k = 0; k < nsteps; ++k) {                                            // multigrid.cpp:165
-        MGB_TRY(s->form_rhs(nullptr));                                            // :167
+        MGB_TRY(s->form_rhs(nullptr, false));                                     // :167
         MGB_TRY(s->solve(infos ? &infos[k] : nullptr));                           // :169
     }
     return MGB200_OK;
@@ -1189,7 +1332,7 @@ static int timestepper_common(double* uT, const double* u0, const double* v1, co
     mgb200_solve_info info;
     std::memset(&info, 0, sizeof(info));
     for (int k = 0; rc == MGB200_OK && k < nsteps; ++k) {
-        rc = s->form_rhs(nullptr);
+        rc = s->form_rhs(nullptr, false);
         if (rc == MGB200_OK) rc = s->solve(&info);
     }
     if (rc == MGB200_OK) rc = host ? mgb200_get_u_host(s, uT) : mgb200_get_u_device(s, uT, n + 1);   // :175
