@@ -110,32 +110,54 @@ __device__ __forceinline__ void step_barrier() { asm volatile("bar.sync 0;" ::: 
 // The loops are unrolled by GROUP (= 4) steps so that the wait for the next TMA group sits at a
 // fixed place and, for the stage warps, the column parity of every step is a compile-time
 // constant: a step is a serial dependency chain and every branch in it is pure latency.
-template <int ARITH, int P0, bool NORM>
+// ONE loop for both starting parities: the unrolled trip is [even, odd, even, odd]; a warp whose
+// first row has odd column parity peels one step and then runs the same trips one step out of
+// phase, so its group wait sits after the third step instead of the fourth (a loop-invariant
+// predicate).  Half the stage code: the hot loops of all roles share the SM's instruction cache.
+template <int ARITH, bool NORM, bool PF>
 __device__ __forceinline__ void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
     const bool feeds_store = (st.idx == 2 * p.K - 1);   // its rows go to the bulk-store engine: generic -> async proxy
     const int t1 = last_step(p, tl);
     int t = first_step(tl);
+    const bool shifted = st.par != 0;
+    if (shifted && t <= t1) {
+        stage_step<ARITH, 1, NORM>(p, geo, sm, st);
+        if (feeds_store) sp_fence_async();
+        stage_flip(st);
+        end_step(tl, geo, sm, st, t);
+        step_barrier();
+        ++t;
+    }
+    D2 f, w1, w2;
+    if (PF && t + 3 <= t1) stage_fetch<0>(geo, sm, st, f, w1, w2);
     for (; t + 3 <= t1; t += 4) {
-        stage_step<ARITH, P0, NORM>(p, geo, sm, st);
+        // rhs / v1 / v2 of the NEXT step are fetched before the step barrier (they do not depend
+        // on the other stages), so their shared-memory latency overlaps the wait
+        if (PF) stage_compute<ARITH, 0, NORM>(p, geo, sm, st, f, w1, w2); else stage_step<ARITH, 0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
+        if (PF) stage_fetch<1>(geo, sm, st, f, w1, w2);
         step_barrier();
-        stage_step<ARITH, P0 ^ 1, NORM>(p, geo, sm, st);
+        if (PF) stage_compute<ARITH, 1, NORM>(p, geo, sm, st, f, w1, w2); else stage_step<ARITH, 1, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
+        if (PF) stage_fetch<0>(geo, sm, st, f, w1, w2);
         step_barrier();
-        stage_step<ARITH, P0, NORM>(p, geo, sm, st);
+        if (PF) stage_compute<ARITH, 0, NORM>(p, geo, sm, st, f, w1, w2); else stage_step<ARITH, 0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
+        if (shifted) wait_group(tl, sm, st, t + 2);
+        if (PF) stage_fetch<1>(geo, sm, st, f, w1, w2);
         step_barrier();
-        stage_step<ARITH, P0 ^ 1, NORM>(p, geo, sm, st);
+        if (PF) stage_compute<ARITH, 1, NORM>(p, geo, sm, st, f, w1, w2); else stage_step<ARITH, 1, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
         advance_row(geo, st);
-        wait_group(tl, sm, st, t + 3);
+        if (!shifted) wait_group(tl, sm, st, t + 3);
+        if (PF && t + 7 <= t1) stage_fetch<0>(geo, sm, st, f, w1, w2);
         step_barrier();
     }
-    st.par = P0;
+    st.par = 0;
     for (; t <= t1; ++t) {
         if (st.par) stage_step<ARITH, 1, NORM>(p, geo, sm, st); else stage_step<ARITH, 0, NORM>(p, geo, sm, st);
         if (feeds_store) sp_fence_async();
@@ -159,28 +181,38 @@ __device__ __forceinline__ void role_loop(const Params& p, const Tile& tl, const
     for (; t <= t1; ++t) { work(t); end_step(tl, geo, sm, st, t); step_barrier(); }
 }
 
-template <int ARITH>
+// FLAVOUR: what the pass does besides smoothing, known when the kernel is chosen.  Each flavour is
+// its own kernel image holding only the role loops it runs: the hot loops of all roles have to
+// share the SM's instruction cache, and a step is too short to hide a miss.
+//   PRE   prolong + correct role present (first pass of an up leg)
+//   POSTK epilogue kind (POST_NONE / POST_INJECT / POST_NORM2)
+#ifndef MGB200_SP_STAGE_PREFETCH
+#define MGB200_SP_STAGE_PREFETCH 1   // stage warps fetch the next step's rhs / v1 / v2 before the step barrier
+#endif
+template <int ARITH, bool PRE, int POSTK>
 __device__ __forceinline__ void run_tile(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st, int lane)
 {
+    constexpr bool PF = MGB200_SP_STAGE_PREFETCH != 0;
+    auto idle = [](int) {};
     if (st.role == ROLE_STAGE) {
-        if (st.nhi >= st.nlo) {          // last stage of a norm pass: also sums its own colour's residuals
-            if (st.par) stage_loop<ARITH, 1, true>(p, tl, geo, sm, st);
-            else stage_loop<ARITH, 0, true>(p, tl, geo, sm, st);
+        if (POSTK == POST_NORM2 && st.nhi >= st.nlo) {   // last stage of a norm pass: also sums its own colour's residuals
+            stage_loop<ARITH, POSTK == POST_NORM2, PF>(p, tl, geo, sm, st);
         } else {
-            if (st.par) stage_loop<ARITH, 1, false>(p, tl, geo, sm, st);
-            else stage_loop<ARITH, 0, false>(p, tl, geo, sm, st);
+            stage_loop<ARITH, false, PF>(p, tl, geo, sm, st);
         }
     } else if (st.role == ROLE_PRE) {
-        role_loop(p, tl, geo, sm, st, [&](int) { pre_step(p, tl, geo, sm, st); if (p.K == 0) sp_fence_async(); });
+        if (PRE) role_loop(p, tl, geo, sm, st, [&](int) { pre_step(p, tl, geo, sm, st); if (p.K == 0) sp_fence_async(); });
+        else role_loop(p, tl, geo, sm, st, idle);
     } else if (st.role == ROLE_POST) {
-        if (st.par) role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 1>(p, tl, geo, sm, st); });
-        else role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 0>(p, tl, geo, sm, st); });
+        if (POSTK == POST_NONE || (POSTK == POST_INJECT && st.par)) role_loop(p, tl, geo, sm, st, idle);
+        else if (st.par) role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 1, POSTK>(p, tl, geo, sm, st); });
+        else role_loop(p, tl, geo, sm, st, [&](int) { post_step<ARITH, 0, POSTK>(p, tl, geo, sm, st); });
     } else {
         role_loop(p, tl, geo, sm, st, [&](int t) { producer_step(p, tl, geo, sm, st, t); });
     }
 }
 
-template <int ARITH>
+template <int ARITH, bool PRE, int POSTK>
 __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constant__ Params p)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -204,10 +236,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_stream_pass(const __grid_constan
     if (warp == PRODUCER_WARP) producer_prologue(p, tl, geo, sm);
     ThreadState st = init_thread(p, tl, geo, warp * 32 + lane);
     wait_first_row(sm);
-    run_tile<ARITH>(p, tl, geo, sm, st, lane);
+    run_tile<ARITH, PRE, POSTK>(p, tl, geo, sm, st, lane);
     if (warp == PRODUCER_WARP && sp_elect()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (p.post == POST_NORM2) {
+    if (POSTK == POST_NORM2) {
         const double tot = block_sum(st.acc, scratch);
         if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
     }
@@ -253,6 +285,21 @@ static const Plan& plan_for(long n, long nrows, int K)
     return it->second;
 }
 
+// the kernel image of a pass flavour
+using PassKernel = void (*)(const Params);
+template <int ARITH>
+static PassKernel pass_kernel_of(bool pre, int post)
+{
+    if (pre) return post == POST_NORM2 ? k_stream_pass<ARITH, true, POST_NORM2> : post == POST_INJECT ? k_stream_pass<ARITH, true, POST_INJECT>
+                                                                                                   : k_stream_pass<ARITH, true, POST_NONE>;
+    return post == POST_NORM2 ? k_stream_pass<ARITH, false, POST_NORM2> : post == POST_INJECT ? k_stream_pass<ARITH, false, POST_INJECT>
+                                                                                             : k_stream_pass<ARITH, false, POST_NONE>;
+}
+static PassKernel pass_kernel(int arith, bool pre, int post)
+{
+    return arith == MGB200_ARITH_EXACT ? pass_kernel_of<MGB200_ARITH_EXACT>(pre, post) : pass_kernel_of<MGB200_ARITH_FAST>(pre, post);
+}
+
 }  // namespace sp
 
 using namespace sp;
@@ -264,8 +311,10 @@ int stream_pass_init()
     int dev = 0;
     MGB_CUDA(cudaGetDevice(&dev));
     MGB_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
-    MGB_CUDA(cudaFuncSetAttribute(k_stream_pass<MGB200_ARITH_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MGB_CUDA(cudaFuncSetAttribute(k_stream_pass<MGB200_ARITH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    for (int arith = 0; arith < 2; ++arith)
+        for (int pre = 0; pre < 2; ++pre)
+            for (int post = 0; post < 3; ++post)
+                MGB_CUDA(cudaFuncSetAttribute(pass_kernel(arith, pre != 0, post), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     MGB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -318,8 +367,7 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
         }
         e = &it->second;
     }
-    if (a.arith == MGB200_ARITH_EXACT) k_stream_pass<MGB200_ARITH_EXACT><<<e->grid, THREADS, e->smem, s>>>(e->p);
-    else k_stream_pass<MGB200_ARITH_FAST><<<e->grid, THREADS, e->smem, s>>>(e->p);
+    pass_kernel(a.arith, e->p.pre != 0, e->p.post)<<<e->grid, THREADS, e->smem, s>>>(e->p);
     return check_launch("k_stream_pass");
 }
 

@@ -304,7 +304,7 @@ SP_FN ThreadState init_thread(const Params& p, const Tile& tl, const Geo& geo, i
 // nodes of the OTHER run: from kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd
 // columns: E[kk], E[kk+1], E[kk+2]).
 template <int ARITH, int PAR, bool NORM = false>
-SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
+SP_FN void stage_compute(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st, const D2 f, const D2 w1, const D2 w2)
 {
     const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
     const unsigned c = st.a_cur + po;
@@ -313,7 +313,6 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
     const D2 up = st.c_up, m = st.c_mid;
     const D2 dn = sp_lds2(sm, st.a_next + po);
     const double x = sp_side_neighbour<PAR ? 1 : -1>(sm, m, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u));
-    const D2 f = sp_lds2(sm, c + geo.ringb), w1 = sp_lds2(sm, c + 2u * geo.ringb), w2 = sp_lds2(sm, c + 3u * geo.ringb);
     const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
     const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
     const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
@@ -335,6 +334,23 @@ SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadSta
         if (st.nmask[PAR] & 2u) st.acc += r1 * r1;
     }
     st.c_up = m; st.c_mid = dn;
+}
+
+// rhs, v1, v2 of the nodes a step updates: read-only ring rows, independent of what the other
+// stages store in the same step (so they may be fetched before the step barrier)
+template <int PAR>
+SP_FN void stage_fetch(const Geo& geo, const Smem& sm, const ThreadState& st, D2& f, D2& w1, D2& w2)
+{
+    const unsigned c = st.a_cur + (PAR ? geo.swkb : 0u);
+    f = sp_lds2(sm, c + geo.ringb); w1 = sp_lds2(sm, c + 2u * geo.ringb); w2 = sp_lds2(sm, c + 3u * geo.ringb);
+}
+
+template <int ARITH, int PAR, bool NORM = false>
+SP_FN void stage_step(const Params& p, const Geo& geo, const Smem& sm, ThreadState& st)
+{
+    D2 f, w1, w2;
+    stage_fetch<PAR>(geo, sm, st, f, w1, w2);
+    stage_compute<ARITH, PAR, NORM>(p, geo, sm, st, f, w1, w2);
 }
 
 // prolongation + correction of row t (gs.cpp:238-241 fused with multigrid.cpp:83), interior nodes.
@@ -379,14 +395,16 @@ SP_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem&
 
 // residual epilogue on finished row q, one node per lane (PAR = its column parity): injection into
 // the coarse rhs (even columns of even rows) or sum of squares
-template <int ARITH, int PAR>
+// POSTK: the pass's epilogue kind if known at compile time (the kernel is specialised per flavour), -1: p.post
+template <int ARITH, int PAR, int POSTK = -1>
 SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, ThreadState& st)
 {
+    const int post = POSTK >= 0 ? POSTK : p.post;
     const int q = st.row;
     if (q < st.lo || q > st.hi) return;
-    if (p.post == POST_INJECT && (q & 1)) return;
+    if (post == POST_INJECT && (q & 1)) return;
     // norm after smoothing: the last half-sweep's colour ((i+j) odd) is summed by the last stage itself
-    if (p.post == POST_NORM2 && p.K > 0 && ((q + PAR) & 1)) return;
+    if (post == POST_NORM2 && p.K > 0 && ((q + PAR) & 1)) return;
     const unsigned po = PAR ? geo.swkb : 0u;
     const unsigned c = st.a_cur + po;                     // the node itself
     const unsigned o = st.a_cur + (geo.swkb - po);        // the other run at the same pair index
@@ -395,7 +413,7 @@ SP_FN void post_step(const Params& p, const Tile& tl, const Geo& geo, const Smem
     const double lf = sp_lds1(sm, PAR ? o : o - 8u), rt = sp_lds1(sm, PAR ? o + 8u : o);
     const Coef4 k = Arith<ARITH>::coef(sp_lds1(sm, c + 2u * geo.ringb), sp_lds1(sm, c + 3u * geo.ringb), p.st);
     const double rv = Arith<ARITH>::residual(sp_lds1(sm, c + geo.ringb), u, up, lf, dn, rt, k, p.st);
-    if (p.post == POST_INJECT) {
+    if (post == POST_INJECT) {
         const long kg = (long)tl.k0 + st.kk;
         p.crhs[((long)(q >> 1) - p.crow0) * p.cpitch + (kg & 1) * p.codd + (kg >> 1)] = rv;       // gs.cpp:283
     } else {
