@@ -9,5 +9,5 @@ missing.
 """
 from .api import (  # noqa: F401
     comm_unique_id, slab_plan, ARITH_EXACT, ARITH_FAST, PLAN_FUSED, PLAN_UNFUSED, MgError, Options, SolveInfo, Solver, lib, maxlvl_for, ops,
-    release_cached, timestepper_host,
+    release_cached, timestepper_device, timestepper_host,
 )

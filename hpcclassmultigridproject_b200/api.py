@@ -309,6 +309,15 @@ def release_cached():
     _ck(lib().mgb200_release_cached())
 
 
+def timestepper_device(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape=1, **opts):
+    """timestepper(...) of multigrid.cu:130 on DEVICE arrays (ld = n+1)."""
+    o = default_options(**opts)
+    info = SolveInfo()
+    _ck(lib().mgb200_timestepper_device(_ptr(uT), _ptr(u0), _ptr(v1), _ptr(v2), nu, maxlvl, n, dt, T, dx, tol, shape,
+                                        C.byref(o), C.byref(info)))
+    return info
+
+
 def timestepper_host(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape=1, **opts):
     """timestepper(uT,u0,v1,v2,nu,maxlvl,n,dt,T,dx,tol,shape) of multigrid.cpp:124 on HOST arrays."""
     o = default_options(**opts)

@@ -155,6 +155,9 @@ struct mgb200_solver {
     LoopState* d_loop = nullptr;
     LoopState* h_loop = nullptr;       // pinned
     int  build_loop_graph();
+    LoopState* h_steps = nullptr;      // pinned: loop state of every step of a multi-step run
+    int h_steps_cap = 0;
+    int  timestep(int nsteps, mgb200_solve_info* infos);
     bool device_loop() const { return opt.use_graph && !loop_failed && (P == 1 || p2p); }
     long launches = 0;
     bool have_fields = false, have_rhs = false;
@@ -235,6 +238,7 @@ void mgb200_solver::release()
     if (loop_exec) { cudaGraphExecDestroy(loop_exec); loop_exec = nullptr; }
     cudaFree(d_loop); d_loop = nullptr;
     if (h_loop) { cudaFreeHost(h_loop); h_loop = nullptr; }
+    if (h_steps) { cudaFreeHost(h_steps); h_steps = nullptr; h_steps_cap = 0; }
     if (stream) cudaStreamSynchronize(stream);
     for (void* m : ipc_mapped) cudaIpcCloseMemHandle(m);     // the neighbours' memory first, then ours
     ipc_mapped.clear();
@@ -920,6 +924,56 @@ int mgb200_solver::solve(mgb200_solve_info* info)
     return MGB200_OK;
 }
 
+// the time loop (multigrid.cpp:165-172).  With the device-side solve loop nothing in a step needs
+// the host: compute_rhs, the solve graph and an asynchronous copy of the loop state are enqueued for
+// all steps back to back and the host synchronises once at the end.
+int mgb200_solver::timestep(int nsteps, mgb200_solve_info* infos)
+{
+    if (nsteps <= 0) return MGB200_OK;
+    int k0 = 0;
+    if (device_loop() && !loop_exec) {
+        // first use: the graph is captured inside solve(), after the first compute_rhs
+        MGB_TRY(form_rhs(nullptr, false));                                        // :167
+        MGB_TRY(solve(infos ? &infos[0] : nullptr));                              // :169
+        k0 = 1;
+    }
+    if (!(device_loop() && loop_exec)) {
+        for (int k = k0; k < nsteps; ++k) {
+            MGB_TRY(form_rhs(nullptr, false));
+            MGB_TRY(solve(infos ? &infos[k] : nullptr));
+        }
+        return MGB200_OK;
+    }
+    const int todo = nsteps - k0;
+    if (todo <= 0) return MGB200_OK;
+    if (h_steps_cap < todo) {
+        if (h_steps) cudaFreeHost(h_steps);
+        h_steps = nullptr; h_steps_cap = 0;
+        MGB_CUDA(cudaMallocHost(&h_steps, (size_t)todo * sizeof(LoopState)));
+        h_steps_cap = todo;
+    }
+    for (int k = 0; k < todo; ++k) {
+        MGB_TRY(form_rhs(nullptr, false));
+        MGB_CUDA(cudaGraphLaunch(loop_exec, stream));
+        MGB_CUDA(cudaMemcpyAsync(&h_steps[k], d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, stream));
+    }
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    norm_is_res0 = false; res0_on_host = true;
+    for (int k = 0; k < todo; ++k) {
+        const LoopState& ls = h_steps[k];
+        const int it = ls.iter;
+        launches += 1 + (long)it * loop_kernels;
+        res0 = ls.res0; res = ls.hist[it];
+        if (infos) {
+            mgb200_solve_info& info = infos[k0 + k];
+            std::memset(&info, 0, sizeof(info));
+            for (int c = 0; c <= it; ++c) info.hist[c] = ls.hist[c];
+            info.cycles = it; info.res0 = res0; info.res = res; info.converged = (res / res0 <= tol) ? 1 : 0;
+        }
+    }
+    return MGB200_OK;
+}
+
 int mgb200_solver::get_u_natural(double* dst_dev, long ld)
 {
     Level& g = lv[0];
@@ -1152,11 +1206,7 @@ int mgb200_solve(mgb200_solver* s, mgb200_solve_info* info)
 int mgb200_timestep(mgb200_solver* s, int nsteps, mgb200_solve_info* infos)
 {
     if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
-    for (int k = 0; k < nsteps; ++k) {                                            // multigrid.cpp:165
-        MGB_TRY(s->form_rhs(nullptr, false));                                     // :167
-        MGB_TRY(s->solve(infos ? &infos[k] : nullptr));                           // :169
-    }
-    return MGB200_OK;
+    return s->timestep(nsteps, infos);                                            // multigrid.cpp:165-172
 }
 
 int mgb200_get_u_device(mgb200_solver* s, double* u, long ld)
@@ -1331,9 +1381,10 @@ static int timestepper_common(double* uT, const double* u0, const double* v1, co
     const int nsteps = (int)(T / dt);                                             // multigrid.cpp:165
     mgb200_solve_info info;
     std::memset(&info, 0, sizeof(info));
-    for (int k = 0; rc == MGB200_OK && k < nsteps; ++k) {
-        rc = s->form_rhs(nullptr, false);
-        if (rc == MGB200_OK) rc = s->solve(&info);
+    if (rc == MGB200_OK && nsteps > 0) {
+        std::vector<mgb200_solve_info> infos((size_t)nsteps);
+        rc = s->timestep(nsteps, infos.data());
+        if (rc == MGB200_OK) info = infos.back();
     }
     if (rc == MGB200_OK) rc = host ? mgb200_get_u_host(s, uT) : mgb200_get_u_device(s, uT, n + 1);   // :175
     if (last) *last = info;
