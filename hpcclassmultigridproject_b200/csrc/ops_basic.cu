@@ -97,6 +97,65 @@ __global__ void __launch_bounds__(TPB) k_compute_rhs(double* __restrict__ rhs, c
     }
 }
 
+// compute_rhs for the colour-split layout (the solver's own arrays): one thread owns two column
+// pairs (four nodes: even columns 2k, 2k+2 in the E run, odd columns 2k+1, 2k+3 in the O run) and
+// walks down a band of rows with the three rows of u it needs in registers.  Every global access
+// is a 16-byte vector, u is read once (plus two halo rows per band), horizontal neighbours across
+// lanes come from shuffles.  Same operands in the same order as k_compute_rhs: identical rhs.
+constexpr int RHS_TPB = 128, RHS_ROWS = 32;
+template <int ARITH, bool WITH_RES0>
+__global__ void __launch_bounds__(RHS_TPB) k_compute_rhs_split(double* __restrict__ rhs, const double* __restrict__ u,
+                                                               const double* __restrict__ v1, const double* __restrict__ v2,
+                                                               long n, Layout L, Stencil st, double* __restrict__ partials,
+                                                               long ilo, long ihi)
+{
+    __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31;
+    const long k = 2 * ((long)blockIdx.x * RHS_TPB + threadIdx.x);      // first of the thread's two pairs
+    const long r0 = ilo + (long)blockIdx.y * RHS_ROWS;
+    const long r1 = r0 + RHS_ROWS - 1 < ihi ? r0 + RHS_ROWS - 1 : ihi;
+    const long nh = n / 2;                                               // E run: k = 0..nh, O run: k = 0..nh-1
+    const bool live = k <= nh;                                           // (the layout's slack covers k+1)
+    // interior columns 1..n-1
+    const bool okE0 = live && k >= 1 && 2 * k <= n - 1, okE1 = live && 2 * (k + 1) <= n - 1;
+    const bool okO0 = live && 2 * k + 1 <= n - 1, okO1 = live && 2 * k + 3 <= n - 1;
+    auto ldE = [&](const double* a, long i) { return live ? *reinterpret_cast<const double2*>(a + (i - L.row0) * L.pitch + k) : make_double2(0.0, 0.0); };
+    auto ldO = [&](const double* a, long i) { return live ? *reinterpret_cast<const double2*>(a + (i - L.row0) * L.pitch + L.odd + k) : make_double2(0.0, 0.0); };
+    double acc = 0.0;
+    double2 upE = ldE(u, r0 - 1), upO = ldO(u, r0 - 1), cE = ldE(u, r0), cO = ldO(u, r0);
+    for (long i = r0; i <= r1; ++i) {
+        const double2 dnE = ldE(u, i + 1), dnO = ldO(u, i + 1);
+        const double2 aE = ldE(v1, i), aO = ldO(v1, i), bE = ldE(v2, i), bO = ldO(v2, i);
+        // E[k]'s left neighbour is O[k-1] (previous lane's cO.y), O[k+1]'s right one is E[k+2] (next lane's cE.x)
+        double lfE = __shfl_up_sync(0xffffffffu, cO.y, 1), rtO = __shfl_down_sync(0xffffffffu, cE.x, 1);
+        if (lane == 0 && okE0) lfE = u[(i - L.row0) * L.pitch + L.odd + k - 1];
+        if (lane == 31 && okO1) rtO = u[(i - L.row0) * L.pitch + k + 2];
+        const Coef4 kE0 = Arith<ARITH>::coef(aE.x, bE.x, st), kE1 = Arith<ARITH>::coef(aE.y, bE.y, st);
+        const Coef4 kO0 = Arith<ARITH>::coef(aO.x, bO.x, st), kO1 = Arith<ARITH>::coef(aO.y, bO.y, st);
+        const double fE0 = Arith<ARITH>::rhs(cE.x, upE.x, lfE, dnE.x, cO.x, kE0, st);
+        const double fE1 = Arith<ARITH>::rhs(cE.y, upE.y, cO.x, dnE.y, cO.y, kE1, st);
+        const double fO0 = Arith<ARITH>::rhs(cO.x, upO.x, cE.x, dnO.x, cE.y, kO0, st);
+        const double fO1 = Arith<ARITH>::rhs(cO.y, upO.y, cE.y, dnO.y, rtO, kO1, st);
+        double* rowp = rhs + (i - L.row0) * L.pitch;
+        if (okE0 && okE1) *reinterpret_cast<double2*>(rowp + k) = make_double2(fE0, fE1);
+        else { if (okE0) rowp[k] = fE0; if (okE1) rowp[k + 1] = fE1; }
+        if (okO0 && okO1) *reinterpret_cast<double2*>(rowp + L.odd + k) = make_double2(fO0, fO1);
+        else { if (okO0) rowp[L.odd + k] = fO0; if (okO1) rowp[L.odd + k + 1] = fO1; }
+        if (WITH_RES0) {
+            // row-major order of the four nodes: columns 2k, 2k+1, 2k+2, 2k+3
+            if (okE0) { const double rv = Arith<ARITH>::residual(fE0, cE.x, upE.x, lfE, dnE.x, cO.x, kE0, st); acc += rv * rv; }
+            if (okO0) { const double rv = Arith<ARITH>::residual(fO0, cO.x, upO.x, cE.x, dnO.x, cE.y, kO0, st); acc += rv * rv; }
+            if (okE1) { const double rv = Arith<ARITH>::residual(fE1, cE.y, upE.y, cO.x, dnE.y, cO.y, kE1, st); acc += rv * rv; }
+            if (okO1) { const double rv = Arith<ARITH>::residual(fO1, cO.y, upO.y, cE.y, dnO.y, rtO, kO1, st); acc += rv * rv; }
+        }
+        upE = cE; upO = cO; cE = dnE; cO = dnO;
+    }
+    if (WITH_RES0) {
+        const double t = block_sum(acc, scratch);
+        if (threadIdx.x == 0) partials[(long)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_square_partials(const double* __restrict__ a, long n, Layout L,
                                                          double* __restrict__ partials)
 {
@@ -327,6 +386,19 @@ int ops_basic_init()
 }
 
 // ---------------------------------------------------------------------------------------------
+// the colour-split layout of a level (common.cuh: split_layout) as opposed to a natural (row-major) one
+static bool is_split(const Layout& L, long n) { const Layout S = split_layout(n); return L.odd == S.odd && L.pitch == S.pitch && L.odd > 0; }
+static dim3 rhs_split_grid(long n, long nrows)
+{
+    const long pairs = n / 2 + 1;
+    return dim3((unsigned)((pairs + 2 * RHS_TPB - 1) / (2 * RHS_TPB)), (unsigned)((nrows + RHS_ROWS - 1) / RHS_ROWS), 1);
+}
+long compute_rhs_partials_count(long n, long nrows, Layout L)
+{
+    if (is_split(L, n)) { const dim3 g = rhs_split_grid(n, nrows); return (long)g.x * g.y; }
+    return rows_partials_count(n, nrows);
+}
+
 long residual_partials_count(long n)
 {
     dim3 g = tile_grid(n - 1, n - 1);
@@ -374,6 +446,17 @@ int launch_compute_rhs(double* rhs, const double* u, const double* v1, const dou
     if (n < 2) return MGB200_OK;
     const long ilo = row_lo < 1 ? 1 : row_lo, ihi = (row_hi < 0 || row_hi > n - 1) ? n - 1 : row_hi;
     if (ihi < ilo) return MGB200_OK;
+    if (is_split(L, n)) {
+        const dim3 g = rhs_split_grid(n, ihi - ilo + 1);
+        if (arith == MGB200_ARITH_EXACT) {
+            if (partials) k_compute_rhs_split<MGB200_ARITH_EXACT, true><<<g, RHS_TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+            else k_compute_rhs_split<MGB200_ARITH_EXACT, false><<<g, RHS_TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+        } else {
+            if (partials) k_compute_rhs_split<MGB200_ARITH_FAST, true><<<g, RHS_TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+            else k_compute_rhs_split<MGB200_ARITH_FAST, false><<<g, RHS_TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);
+        }
+        return check_launch("k_compute_rhs_split");
+    }
     dim3 g = tile_grid(ihi - ilo + 1, n - 1);
     if (arith == MGB200_ARITH_EXACT) {
         if (partials) k_compute_rhs<MGB200_ARITH_EXACT, true><<<g, TPB, 0, s>>>(rhs, u, v1, v2, n, L, st, partials, ilo, ihi);

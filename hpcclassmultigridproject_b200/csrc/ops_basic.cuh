@@ -24,6 +24,8 @@ long residual_partials_count(long n);
 int launch_compute_rhs(double* rhs, const double* u, const double* v1, const double* v2, long n, Layout L,
                        const Stencil& st, int arith, double* partials, cudaStream_t s, long row_lo = 1, long row_hi = -1);
 long rows_partials_count(long n, long nrows);
+// entries launch_compute_rhs writes into `partials` for a band of nrows rows in layout L
+long compute_rhs_partials_count(long n, long nrows, Layout L);
 // sum of squares over the interior of a -> partials (same count as residual_partials_count)
 int launch_square_partials(const double* a, long n, Layout L, double* partials, cudaStream_t s);
 // out[0] = sum(partials[0..count)) in a fixed order (single block)

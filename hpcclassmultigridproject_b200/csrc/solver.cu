@@ -862,11 +862,11 @@ int mgb200_solver::form_rhs(double* res0_out, bool sync)
     const long before = launch_counter();
     if (P == 1) {
         MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream));
-        MGB_TRY(launch_reduce_partials(d_partials, residual_partials_count(g.n), d_norm2, stream));
+        MGB_TRY(launch_reduce_partials(d_partials, compute_rhs_partials_count(g.n, g.n - 1, g.L), d_norm2, stream));
     } else {
         const long ilo = g.own_lo < 1 ? 1 : g.own_lo, ihi = g.own_hi > g.n - 1 ? g.n - 1 : g.own_hi;
         MGB_TRY(launch_compute_rhs(g.rhs, g.u[g.cur], g.v1, g.v2, g.n, g.L, g.st, opt.arith, d_partials, stream, ilo, ihi));
-        MGB_TRY(launch_reduce_partials(d_partials, rows_partials_count(g.n, ihi - ilo + 1), d_norm2, stream));
+        MGB_TRY(launch_reduce_partials(d_partials, compute_rhs_partials_count(g.n, ihi - ilo + 1, g.L), d_norm2, stream));
         MGB_TRY(allreduce_norm());
         MGB_TRY(exchange_halo(g, g.rhs));
     }
