@@ -20,7 +20,8 @@ class MgError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("shape", C.c_int), ("niter", C.c_int), ("coarse_maxit", C.c_int),
                 ("coarse_tol", C.c_double), ("max_cycle", C.c_int), ("arith", C.c_int), ("plan", C.c_int),
-                ("correct_towers", C.c_int), ("use_graph", C.c_int), ("device", C.c_int), ("reserved", C.c_int * 8)]
+                ("correct_towers", C.c_int), ("use_graph", C.c_int), ("device", C.c_int), ("restriction", C.c_int),
+                ("reserved", C.c_int * 7)]
 
 
 class SolveInfo(C.Structure):
@@ -56,6 +57,7 @@ def lib():
     L.mgb200_prolongation.argtypes = [_vp, _l, _vp, _l, _l, _vp]
     L.mgb200_prolong_correct.argtypes = [_vp, _l, _vp, _l, _l, _vp]
     L.mgb200_vecadd.argtypes = [_vp, _vp, _vp, _l, _l, _vp]
+    L.mgb200_restriction_fw.argtypes = L.mgb200_restriction.argtypes
     L.mgb200_initial_conditions.argtypes = [_vp, _vp, _vp, _l, _l, _d, _vp]
     L.mgb200_default_options.argtypes = [C.POINTER(Options)]
     L.mgb200_default_options.restype = None
@@ -165,6 +167,11 @@ class _Ops:
 
     def restriction(self, coarse, fine, nf, stream=None):
         _ck(lib().mgb200_restriction(_ptr(coarse), self._ld(coarse), _ptr(fine), self._ld(fine), nf, stream))
+        return coarse
+
+    def restriction_fw(self, coarse, fine, nf, stream=None):
+        """opt-in full weighting (gs.cpp:277-280, commented out in the reference)"""
+        _ck(lib().mgb200_restriction_fw(_ptr(coarse), self._ld(coarse), _ptr(fine), self._ld(fine), nf, stream))
         return coarse
 
     def prolongation(self, fine, coarse, nc, stream=None):

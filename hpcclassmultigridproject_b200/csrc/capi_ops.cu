@@ -111,6 +111,12 @@ int mgb200_restriction(double* coarse, long ldc, const double* fine, long ldf, l
     return launch_restrict(coarse, natural_layout(ldc), fine, natural_layout(ldf), nf, (cudaStream_t)stream);
 }
 
+int mgb200_restriction_fw(double* coarse, long ldc, const double* fine, long ldf, long nf, void* stream)
+{
+    if (!coarse || !fine || nf < 2 || (nf & 1) || ldf < nf + 1 || ldc < nf / 2 + 1) return fail(MGB200_ERR_INVALID, "restriction_fw: bad argument");
+    return launch_restrict_fw(coarse, natural_layout(ldc), fine, natural_layout(ldf), nf, false, (cudaStream_t)stream);
+}
+
 int mgb200_prolongation(double* fine, long ldf, const double* coarse, long ldc, long nc, void* stream)
 {
     if (!coarse || !fine || nc < 1 || ldf < 2 * nc + 1 || ldc < nc + 1) return fail(MGB200_ERR_INVALID, "prolongation: bad argument");

@@ -197,6 +197,31 @@ __global__ void __launch_bounds__(TPB) k_restrict(double* __restrict__ coarse, L
     }
 }
 
+// full weighting as sketched in gs.cpp:277-280 (commented out in the reference; opt-in here):
+// [1 2 1; 2 4 2; 1 2 1]/16 on the coarse interior, grouped by fine rows as written there
+// (x/16 == x*0.0625 exactly); the boundary is injected.
+template <bool INTERIOR>
+__global__ void __launch_bounds__(TPB) k_restrict_fw(double* __restrict__ coarse, Layout Lc,
+                                                     const double* __restrict__ fine, Layout Lf, long nc)
+{
+    const long lo = INTERIOR ? 1 : 0, hi = INTERIOR ? nc - 1 : nc;
+    const long J = lo + (long)blockIdx.y * TPB + threadIdx.x;
+    const long I0 = lo + (long)blockIdx.x * ROWS_PER_BLOCK;
+    for (int r = 0; r < ROWS_PER_BLOCK; ++r) {
+        const long I = I0 + r;
+        if (I > hi || J > hi) break;
+        if (I == 0 || J == 0 || I == nc || J == nc) { coarse[Lc.at(I, J)] = fine[Lf.at(2 * I, 2 * J)]; continue; }
+        auto row = [&](long i, double w) {
+            const double s1 = __dadd_rn(__dmul_rn(w, fine[Lf.at(i, 2 * J - 1)]), __dmul_rn(2.0 * w, fine[Lf.at(i, 2 * J)]));
+            return __dmul_rn(__dadd_rn(s1, __dmul_rn(w, fine[Lf.at(i, 2 * J + 1)])), 0.0625);
+        };
+        double t = row(2 * I - 1, 1.0);
+        t = __dadd_rn(t, row(2 * I, 2.0));
+        t = __dadd_rn(t, row(2 * I + 1, 1.0));
+        coarse[Lc.at(I, J)] = t;
+    }
+}
+
 template <bool ADD>
 __global__ void __launch_bounds__(TPB) k_prolong(double* __restrict__ fine, Layout Lf,
                                                  const double* __restrict__ coarse, Layout Lc, long nc)
@@ -494,6 +519,18 @@ int launch_restrict_interior(double* coarse, Layout Lc, const double* fine, Layo
     if (nc < 2) return MGB200_OK;
     k_restrict<true><<<tile_grid(nc - 1, nc - 1), TPB, 0, s>>>(coarse, Lc, fine, Lf, nc);
     return check_launch("k_restrict");
+}
+
+int launch_restrict_fw(double* coarse, Layout Lc, const double* fine, Layout Lf, long nf, bool interior_only, cudaStream_t s)
+{
+    const long nc = nf / 2;
+    if (interior_only) {
+        if (nc < 2) return MGB200_OK;
+        k_restrict_fw<true><<<tile_grid(nc - 1, nc - 1), TPB, 0, s>>>(coarse, Lc, fine, Lf, nc);
+    } else {
+        k_restrict_fw<false><<<tile_grid(nc + 1, nc + 1), TPB, 0, s>>>(coarse, Lc, fine, Lf, nc);
+    }
+    return check_launch("k_restrict_fw");
 }
 
 int launch_prolong(double* fine, Layout Lf, const double* coarse, Layout Lc, long nc, bool add, cudaStream_t s)

@@ -35,6 +35,8 @@ int launch_restrict(double* coarse, Layout Lc, const double* fine, Layout Lf, lo
 // interior-only injection (coarse boundary left untouched)
 int launch_restrict_interior(double* coarse, Layout Lc, const double* fine, Layout Lf, long nf, cudaStream_t s);
 // fine = P(coarse) (add=false) or fine += P(coarse) (add=true)      -- gs.cpp:228-266, multigrid.cpp:83
+// full weighting of gs.cpp:277-280 (commented out in the reference; opt-in): interior stencil, injected boundary
+int launch_restrict_fw(double* coarse, Layout Lc, const double* fine, Layout Lf, long nf, bool interior_only, cudaStream_t s);
 int launch_prolong(double* fine, Layout Lf, const double* coarse, Layout Lc, long nc, bool add, cudaStream_t s);
 int launch_vecadd(double* c, const double* a, const double* b, long n, Layout L, cudaStream_t s);
 // dst(layout Ld) = src(layout Ls) over the (n+1)^2 nodes

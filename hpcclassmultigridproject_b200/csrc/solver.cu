@@ -273,6 +273,8 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "coarsest level must have n <= 64 (on-device coarse solve); raise maxlvl");
     if (opt.shape < 1 || opt.niter < 0 || opt.max_cycle < 0 || opt.max_cycle > 50)
         return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
+    if (opt.restriction != 0 && (opt.restriction != 1 || opt.plan != MGB200_PLAN_UNFUSED))
+        return fail(MGB200_ERR_INVALID, "options.restriction: 0 (injection) or 1 (full weighting, UNFUSED plan only)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
     // the sharded cycle (kernels + NCCL point-to-point groups + all-reduce) is captured like the
@@ -668,7 +670,8 @@ int mgb200_solver::cycle_body(int l)
             MGB_TRY(smooth(g, opt.niter));                                        // :69-72
             double* tmp = g.u[1 - g.cur];                                         // the idle twin is the scratch
             MGB_TRY(launch_residual(tmp, g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, nullptr, stream)); // :73
-            MGB_TRY(launch_restrict_interior(c.rhs, c.L, tmp, g.L, g.n, stream)); // :75
+            if (opt.restriction == 1) MGB_TRY(launch_restrict_fw(c.rhs, c.L, tmp, g.L, g.n, true, stream));   // gs.cpp:277-280, opt-in
+            else MGB_TRY(launch_restrict_interior(c.rhs, c.L, tmp, g.L, g.n, stream)); // :75
             if (l + 1 != maxlvl - 1)                                              // :77 (coarsest zero-fills itself)
                 MGB_CUDA(cudaMemsetAsync(c.u[c.cur], 0, c.elems * sizeof(double), stream));
             MGB_TRY(cycle_body(l + 1));                                           // :79

@@ -85,6 +85,12 @@ int mgb200_compute_rhs(double *rhs, const double *u, long n, long ld, const doub
 int mgb200_restriction(double *coarse, long ldc, const double *fine, long ldf, long nf,
                        void *stream);
 
+/* OPT-IN, not on the reference's active path: the full-weighting restriction the reference sketches
+ * in commented-out lines (gs.cpp:277-280): [1 2 1; 2 4 2; 1 2 1]/16 on the coarse interior, boundary
+ * injected. */
+int mgb200_restriction_fw(double *coarse, long ldc, const double *fine, long ldf, long nf,
+                          void *stream);
+
 /* bilinear interpolation, every one of the (2nc+1)^2 fine nodes written.
  * gs.h:16 prolongation / gscu.h:7 (gs.cpp:228-266, gs.cu:63-81); nc = COARSE n */
 int mgb200_prolongation(double *fine, long ldf, const double *coarse, long ldc, long nc,
@@ -124,7 +130,9 @@ typedef struct mgb200_options {
                                SURVEY.md 8/P1); 1 = true injection of the velocities.  default 0 */
     int    use_graph;       /* capture one cycle into a CUDA graph and replay it; default 1 */
     int    device;          /* CUDA device ordinal, -1 = current; default -1 */
-    int    reserved[8];
+    int    restriction;     /* 0 = injection of the residual (the reference, gs.cpp:283); 1 = full weighting
+                               (gs.cpp:277-280, commented out there).  Opt-in, UNFUSED plan only; default 0 */
+    int    reserved[7];
 } mgb200_options;
 
 typedef struct mgb200_solve_info {

@@ -155,6 +155,25 @@ void orc_restriction(double *coarse, const double *fine, long nf)
             coarse[I * ldc + J] = fine[2 * I * ldf + 2 * J];
 }
 
+/* Full-weighting restriction exactly as sketched in the reference's commented-out lines
+ * gs.cpp:277-280 (never active there, "get this working if time permits"): interior coarse nodes
+ * take the [1 2 1; 2 4 2; 1 2 1]/16 stencil, grouped by fine rows as written there; boundary nodes
+ * (where the sketch would index out of bounds) are injected.  Opt-in only: the reference's active
+ * path is orc_restriction. */
+void orc_restriction_fw(double *coarse, const double *fine, long nf)
+{
+    const long nc = nf / 2, ldc = nc + 1, ldf = nf + 1;
+    for (long I = 0; I <= nc; ++I)
+        for (long J = 0; J <= nc; ++J) {
+            if (I == 0 || J == 0 || I == nc || J == nc) { coarse[I * ldc + J] = fine[2 * I * ldf + 2 * J]; continue; }
+            const double *a = fine + (2 * I - 1) * ldf + 2 * J, *b = a + ldf, *c = b + ldf;
+            double t = (a[-1] + 2 * a[0] + a[1]) / 16;                                     /* :278 */
+            t += (2 * b[-1] + 4 * b[0] + 2 * b[1]) / 16;                                   /* :279 */
+            t += (c[-1] + 2 * c[0] + c[1]) / 16;                                           /* :280 */
+            coarse[I * ldc + J] = t;
+        }
+}
+
 /* ------------------------------------------------------------------------- */
 #define ORC_MAXLVL 32
 #define ORC_NITER 3            /* multigrid.cpp:41  */

@@ -36,6 +36,7 @@ void   orc_gauss_seidel(double *u, const double *rhs, long n, const double *v1,
 void   orc_prolongation(double *fine, const double *coarse, long nc);
 /* out is (nf/2+1)^2, in is (nf+1)^2 */
 void   orc_restriction (double *coarse, const double *fine, long nf);
+void   orc_restriction_fw(double *coarse, const double *fine, long nf);   /* gs.cpp:277-280 (commented out there) */
 
 /* ---- driver (reference multigrid.cpp:17-186) ----------------------------- */
 typedef struct orc_solver orc_solver;

@@ -68,6 +68,7 @@ class Oracle:
             L.orc_gauss_seidel.argtypes = [_dp, _dp, l, _dp, _dp, d, d, d]
             L.orc_prolongation.argtypes = [_dp, _dp, l]
             L.orc_restriction.argtypes = [_dp, _dp, l]
+            L.orc_restriction_fw.argtypes = [_dp, _dp, l]
             L.orc_timestepper.argtypes = [_dp, _dp, _dp, _dp, d, i, i, d, d, d, d, i]
             L.orc_initial_conditions.argtypes = [_dp, _dp, _dp, l, d]
             L.orc_create.argtypes = [l, i, _dp, _dp, _dp, d, d, d, d, i]; L.orc_create.restype = C.c_void_p
@@ -128,6 +129,12 @@ class Oracle:
     def restriction(self, fine, nf):
         coarse = np.zeros((nf // 2 + 1, nf // 2 + 1))
         getattr(self.lib, self.pfx + "restriction")(_p(coarse), _p(fine), nf)
+        return coarse
+
+    def restriction_fw(self, fine, nf):
+        """full weighting of gs.cpp:277-280 (commented out in the reference: restatement only, no _ref twin)"""
+        coarse = np.zeros((nf // 2 + 1, nf // 2 + 1))
+        self.lib.orc_restriction_fw(_p(coarse), _p(np.ascontiguousarray(fine)), nf)
         return coarse
 
     # ---- drivers ---------------------------------------------------------------

@@ -92,6 +92,15 @@ def test_transfer_operators_bitwise(mg, oracle, nc):
     assert np.array_equal(s, base + want)
 
 
+@pytest.mark.parametrize("nf", [2, 4, 32, 130, 512])
+def test_full_weighting_restriction_opt_in(mg, oracle, nf):
+    """gs.cpp:277-280 (commented out in the reference): the opt-in operator against its C restatement"""
+    rng = np.random.default_rng(nf)
+    fine = rng.standard_normal((nf + 1, nf + 1))
+    got = mg.ops.restriction_fw(torch.zeros(nf // 2 + 1, nf // 2 + 1, dtype=torch.float64, device="cuda"), dev(fine), nf)
+    assert np.array_equal(got.cpu().numpy(), oracle.restriction_fw(fine, nf))
+
+
 def test_known_answer_ramp(mg):
     """prolrestest.cpp:76-118"""
     n = 5

@@ -150,6 +150,23 @@ def test_fused_equals_unfused_bitwise(mg, oracle):
         assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=0)
 
 
+def test_full_weighting_option(mg, oracle):
+    """options.restriction = 1 (opt-in, UNFUSED plan): converges to the same solution as the reference's
+    injection; rejected on the fused plan"""
+    n = 256; dx = 1.0 / n; dt = dx / 10
+    u0, v1, v2 = oracle.initial_conditions(n, 2.0)
+    out = []
+    for restriction in (0, 1):
+        with mg.Solver(n, -4e-4, dt, dx, 1e-10, plan=mg.PLAN_UNFUSED, restriction=restriction) as s:
+            s.set_fields_host(u0, v1, v2)
+            infos = s.timestep(3)
+            assert all(i.converged for i in infos)
+            out.append(s.get_u_host())
+    assert rel_l2(out[1], out[0]) <= 1e-8          # two convergent iterations for the same linear system
+    with pytest.raises(Exception):
+        mg.Solver(n, -4e-4, dt, dx, 1e-10, plan=mg.PLAN_FUSED, restriction=1)
+
+
 LARGE = ["large_c2_n4096", "large_n2048_v6", "large_n8192", "large_c3_n16384", "large_c4_n16384"]
 
 

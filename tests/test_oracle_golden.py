@@ -135,3 +135,21 @@ def test_coarse_velocity_tower_quirk(oracle):
             flat2[i * (nq + 1) + j] = flat1[2 * i * (nh + 1) + 2 * j]
     assert np.array_equal(s.v1(2).reshape(-1), flat2[: (nq + 1) ** 2])
     s.close()
+
+
+def test_full_weighting_restatement(oracle):
+    """orc_restriction_fw restates lines the reference keeps commented out (gs.cpp:277-280), so there is
+    no compiled twin to pin it to: check it against the written formula and its defining properties"""
+    rng = np.random.default_rng(7)
+    nf = 16
+    f = rng.standard_normal((nf + 1, nf + 1))
+    c = oracle.restriction_fw(f, nf)
+    I, J = 3, 5
+    want = (f[2*I-1, 2*J-1] + 2*f[2*I-1, 2*J] + f[2*I-1, 2*J+1]) / 16
+    want += (2*f[2*I, 2*J-1] + 4*f[2*I, 2*J] + 2*f[2*I, 2*J+1]) / 16
+    want += (f[2*I+1, 2*J-1] + 2*f[2*I+1, 2*J] + f[2*I+1, 2*J+1]) / 16
+    assert c[I, J] == want
+    assert np.array_equal(c[0, :], f[0, ::2]) and np.array_equal(c[:, -1], f[::2, -1])      # boundary: injection
+    assert np.array_equal(oracle.restriction_fw(np.ones_like(f), nf), np.ones((nf // 2 + 1, nf // 2 + 1)))   # weights sum to 1
+    ramp = np.add.outer(np.arange(nf + 1.0), 2.0 * np.arange(nf + 1.0))
+    assert np.array_equal(oracle.restriction_fw(ramp, nf), ramp[::2, ::2])                   # exact on linear functions
