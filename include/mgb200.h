@@ -156,12 +156,15 @@ int mgb200_destroy(mgb200_solver *s);
  * reference is single-GPU).  Rank 0 calls mgb200_comm_unique_id and the host
  * program broadcasts the 128 bytes (bench.py uses torch.distributed); every rank then calls
  * mgb200_create_sharded on its own device.  Fine levels are cut into row slabs at even rows (own
- * rows + 8 halo rows exchanged with the slab neighbours over NCCL after every streaming pass); levels
- * with fewer than shard_min_rows rows per rank (0 = default 256) run whole on rank 0, fed by a
- * gather of the restricted residual and followed by a scatter of the correction; the residual norm
- * is all-reduced.  The handle is then used like a single-GPU one: set_fields_* take the FULL-SIZE
- * arrays on every rank (each rank keeps its window), get_u_* fill only the rows the rank owns.
- * Fused plan only.  The whole sharded cycle, NCCL calls included, is captured into the CUDA graph.
+ * rows + 8 halo rows exchanged with the slab neighbours after every streaming pass); levels with
+ * fewer than shard_min_rows rows per rank (0 = default 256) run whole on rank 0, fed by a gather of
+ * the restricted residual and followed by a scatter of the correction; the residual norm is summed
+ * over the ranks.  All of these transfers are stores into the peers' memory (CUDA IPC over NVLink)
+ * synchronised by device-side counters; NCCL bootstraps (one all-gather of the IPC handles) and is
+ * the fallback transport (environment MGB200_P2P=0).  One rank per GPU: ranks of one communicator
+ * must not share a device.  The handle is then used like a single-GPU one: set_fields_* take the
+ * FULL-SIZE arrays on every rank (each rank keeps its window), get_u_* fill only the rows the rank
+ * owns; form_rhs / cycle / solve / timestep are collective.  Fused plan only.
  * ------------------------------------------------------------------------------------------ */
 int mgb200_comm_unique_id(unsigned char id[128]);
 int mgb200_create_sharded(mgb200_solver **out, long n, int maxlvl, double nu, double dt, double dx,
@@ -189,9 +192,13 @@ int mgb200_cycle(mgb200_solver *s, double *res);
 /* asynchronous variant (no host read-back): the norm stays on the device until mgb200_last_norm */
 int mgb200_cycle_async(mgb200_solver *s);
 int mgb200_last_norm(mgb200_solver *s, double *res);
-/* mg_outer (multigrid.cpp:97-120) for the current rhs */
+/* mg_outer (multigrid.cpp:97-120) for the current rhs.  With options.use_graph the loop itself runs
+ * on the device (one CUDA graph: k_loop_begin -> WHILE { cycle ; k_loop_check }), the host reads the
+ * loop state once afterwards.  Environment MGB200_DEVICE_LOOP=0 keeps the loop on the host (one
+ * 8-byte read-back per cycle; needed under Nsight Compute). */
 int mgb200_solve(mgb200_solver *s, mgb200_solve_info *info);
-/* nsteps x { compute_rhs ; mg_outer } (multigrid.cpp:165-172).  infos may be NULL, else nsteps entries */
+/* nsteps x { compute_rhs ; mg_outer } (multigrid.cpp:165-172).  infos may be NULL, else nsteps
+ * entries.  All steps are enqueued back to back; the host synchronises once at the end. */
 int mgb200_timestep(mgb200_solver *s, int nsteps, mgb200_solve_info *infos);
 
 /* copy u_0 out: dense DEVICE array with row stride ld / dense HOST array (multigrid.cpp:175) */
