@@ -1,7 +1,9 @@
-// comm.cuh -- one-process-per-GPU communication for the row-slab sharded solver: a thin layer over
-// NCCL (loaded at run time from the process: torch.distributed has already mapped libnccl.so.2, a
-// single-GPU user never needs it).  Point-to-point rows go between slab neighbours, one double is
-// all-reduced per convergence check.
+// comm.cuh -- one-process-per-GPU communication for the row-slab sharded solver.
+//  * a thin layer over NCCL (loaded at run time from the process: torch.distributed has already
+//    mapped libnccl.so.2, a single-GPU user never needs it): bootstrap (all-gather of CUDA IPC
+//    handles) and the fallback transport (send/receive groups, all-reduce);
+//  * the production transport: kernels that store rows into the peers' memory over NVLink and
+//    synchronise through device-side counters (further down).
 #pragma once
 #include "common.cuh"
 

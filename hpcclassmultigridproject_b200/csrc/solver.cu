@@ -277,7 +277,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "options.restriction: 0 (injection) or 1 (full weighting, UNFUSED plan only)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
-    // the sharded cycle (kernels + NCCL point-to-point groups + all-reduce) is captured like the
+    // the sharded cycle (kernels + peer-memory transfers, or NCCL groups as the fallback) is captured like the
     // single-GPU one; MGB200_SHARDED_GRAPH=0 issues everything directly on the stream instead
     if (P > 1) { const char* e = getenv("MGB200_SHARDED_GRAPH"); if (e && atoi(e) == 0) opt.use_graph = 0; }
     if (getenv("MGB200_TRACE")) { tracing = true; opt.use_graph = 0; }

@@ -546,7 +546,7 @@ SP_FN void end_step(const Tile& tl, const Geo& geo, const Smem& sm, ThreadState&
 // band count for the cheapest plan.
 struct Plan { int WK, SWK, nstrips, nbands; long RBAND; };
 
-// resident tiles per SM: one (608 threads x ~90 registers fill the register file)
+// resident tiles per SM: one (736 threads x up to 88 registers fill the register file; 217.5 KB of shared memory)
 inline int tiles_per_sm(int) { return 1; }
 
 // n: level size (columns); nrows: rows this launch produces (n+1 on a single GPU, the slab otherwise)
