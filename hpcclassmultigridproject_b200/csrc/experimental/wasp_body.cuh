@@ -44,7 +44,11 @@ struct Params {
     long pitch, odd, cpitch, codd;
     int K, post, pre;
     int nstrips, nbands;
-    long RB;                            // owned rows per band (bands tile rows 0..n)
+    long RB;                            // owned rows per band (bands tile rows own_lo..own_hi)
+    // row window (row-slab sharding, same meaning as StreamPassArgs): rows own_lo..own_hi are
+    // produced; the fine arrays hold global rows row0.., the coarse arrays global rows crow0..
+    // A whole level is own_lo = 0, own_hi = n, row0 = crow0 = 0.
+    long own_lo, own_hi, row0, crow0;
     Stencil st;
 };
 
@@ -87,9 +91,9 @@ WP_FN Strip make_strip(const Params& p, int strip, int band, int lane)
         if (owned && kk <= p.nhalf - 1) { s.own[1] |= 1u << e; s.oint[1] |= 1u << e; }
     }
     const long hrow = 2 * p.K + 1;
-    s.b0 = (long)band * p.RB;
-    s.b1 = s.b0 + p.RB - 1 < p.n ? s.b0 + p.RB - 1 : p.n;
-    s.R0 = s.b0 - hrow < 0 ? 0 : s.b0 - hrow;
+    s.b0 = p.own_lo + (long)band * p.RB;
+    s.b1 = s.b0 + p.RB - 1 < p.own_hi ? s.b0 + p.RB - 1 : p.own_hi;
+    s.R0 = s.b0 - hrow < 0 ? 0 : s.b0 - hrow;          // (a slab holds at least 2K+1 halo rows per side)
     s.R1 = s.b1 + hrow > p.n ? p.n : s.b1 + hrow;
     return s;
 }
@@ -97,7 +101,7 @@ WP_FN Strip make_strip(const Params& p, int strip, int band, int lane)
 WP_FN V2 ld_run(const Params& p, const Strip& s, const double* a, long row, int par)
 {
     if (!s.live) return V2{0.0, 0.0};
-    return wp_ld2(a + row * p.pitch + (par ? p.odd : 0) + s.k);
+    return wp_ld2(a + (row - p.row0) * p.pitch + (par ? p.odd : 0) + s.k);
 }
 
 WP_FN void st_masked(double* q, V2 v, unsigned m)
@@ -111,7 +115,7 @@ WP_FN double coarse_at(const Params& p, long I, long J)
 {
     const long nc = p.nhalf;
     if (I < 0 || I > nc || J < 0 || J > nc) return 0.0;
-    return p.cu[I * p.cpitch + (J & 1) * p.codd + (J >> 1)];
+    return p.cu[(I - p.crow0) * p.cpitch + (J & 1) * p.codd + (J >> 1)];
 }
 
 // prolongation + correction of the freshly loaded row t (gs.cpp:238-241 + multigrid.cpp:83), interior nodes
@@ -167,7 +171,7 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
                 const double r1 = Arith<ARITH>::residual(f.y, wE[c].y, wE[c + 1].y, n1, wE[c - 1].y, n2, c1, p.st);
                 if (p.post == POST_INJECT) {
                     // coarse node (e/2, kk) for even column 2kk: kk = k is even (coarse even run), k+1 odd
-                    double* row = p.crhs + (e >> 1) * p.cpitch;
+                    double* row = p.crhs + ((e >> 1) - p.crow0) * p.cpitch;
                     if (s.oint[0] & 1u) row[s.k >> 1] = r0;                                   // gs.cpp:283
                     if (s.oint[0] & 2u) row[p.codd + (s.k >> 1)] = r1;
                 } else {
@@ -217,7 +221,7 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
     {
         const long f = t - 2 * K - 1;
         if (f >= s.b0 && f <= s.b1 && (K > 0 || p.pre)) {
-            double* row = p.u_out + f * p.pitch + s.k;
+            double* row = p.u_out + (f - p.row0) * p.pitch + s.k;
             if (s.own[0]) st_masked(row, wE[2 * K + 1], s.own[0]);
             if (s.own[1]) st_masked(row + p.odd, wO[2 * K + 1], s.own[1]);
         }
@@ -260,13 +264,13 @@ WP_FN void run_strip(const Params& p, int tile)
     }
 }
 
-// geometry: strips of OWN pairs over pairs 0..nhalf, bands of RB rows over rows 0..n
-inline void plan(long n, long rows_per_band, int& nstrips, int& nbands, long& RB)
+// geometry: strips of OWN pairs over pairs 0..nhalf, bands of RB rows over the nrows produced rows
+inline void plan(long n, long nrows, long rows_per_band, int& nstrips, int& nbands, long& RB)
 {
     const long npairs = n / 2 + 1;
     nstrips = (int)((npairs + OWN - 1) / OWN);
     RB = rows_per_band < 1 ? 1 : rows_per_band;
-    nbands = (int)((n + 1 + RB - 1) / RB);
+    nbands = (int)((nrows + RB - 1) / RB);
 }
 
 }  // namespace wasp

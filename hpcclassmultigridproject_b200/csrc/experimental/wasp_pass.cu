@@ -70,7 +70,7 @@ const char* mgb200x_last_error(void) { return g_err.c_str(); }
 long mgb200x_wasp_tiles(long n, long rows_per_band)
 {
     int ns, nb; long RB;
-    wasp::plan(n, rows_per_band > 0 ? rows_per_band : 512, ns, nb, RB);
+    wasp::plan(n, n + 1, rows_per_band > 0 ? rows_per_band : 512, ns, nb, RB);
     return (long)ns * nb;
 }
 
@@ -90,7 +90,8 @@ int mgb200x_wasp_pass(long n, const double* u_in, double* u_out, const double* r
     p.u_in = u_in; p.rhs = rhs; p.v1 = v1; p.v2 = v2; p.cu = cu; p.u_out = u_out; p.crhs = crhs; p.partials = partials;
     p.n = n; p.nhalf = n / 2; p.pitch = L.pitch; p.odd = L.odd; p.cpitch = Lc.pitch; p.codd = Lc.odd;
     p.K = K; p.post = post; p.pre = cu ? 1 : 0;
-    wasp::plan(n, rows_per_band > 0 ? rows_per_band : 512, p.nstrips, p.nbands, p.RB);
+    p.own_lo = 0; p.own_hi = n; p.row0 = 0; p.crow0 = 0;          // whole level (slab windows: see wasp_body.cuh)
+    wasp::plan(n, n + 1, rows_per_band > 0 ? rows_per_band : 512, p.nstrips, p.nbands, p.RB);
     p.st = make_stencil(dt, nu, dx);
     const int tiles = p.nstrips * p.nbands;
     const unsigned grid = (unsigned)((tiles + wasp::WARPS_PER_CTA - 1) / wasp::WARPS_PER_CTA);

@@ -75,13 +75,16 @@ extern "C" {
 // all arrays: HOST arrays in the split layout (pitch = 2*odd); returns the number of tiles
 long wasp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const double* u_in, double* u_out, const double* rhs,
                   const double* v1, const double* v2, const double* cu, double* crhs, double* partials, int K, int post,
-                  int arith, double dt, double nu, double dx, long rows_per_band)
+                  int arith, double dt, double nu, double dx, long rows_per_band, long own_lo, long own_hi, long row0, long crow0)
 {
     wasp::Params p{};
     p.u_in = u_in; p.rhs = rhs; p.v1 = v1; p.v2 = v2; p.cu = cu; p.u_out = u_out; p.crhs = crhs; p.partials = partials;
     p.n = n; p.nhalf = n / 2; p.pitch = pitch; p.odd = odd; p.cpitch = cpitch; p.codd = codd;
     p.K = K; p.post = post; p.pre = cu ? 1 : 0;
-    wasp::plan(n, rows_per_band, p.nstrips, p.nbands, p.RB);
+    // own_hi < 0: the whole level; otherwise a row slab (arrays hold global rows row0.. / crow0..)
+    if (own_hi < 0) { own_lo = 0; own_hi = n; row0 = 0; crow0 = 0; }
+    p.own_lo = own_lo; p.own_hi = own_hi; p.row0 = row0; p.crow0 = crow0;
+    wasp::plan(n, own_hi - own_lo + 1, rows_per_band, p.nstrips, p.nbands, p.RB);
     // Stencil exactly as make_stencil (solver.cu)
     volatile double r = 0.5 * dt / (dx * dx);
     volatile double four_r = 4.0 * r;

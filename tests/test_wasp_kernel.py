@@ -38,7 +38,7 @@ def wemu():
                         "-I/usr/local/cuda/include", "-o", so, src[0]], check=True, env=_env())
     lib = C.CDLL(so)
     lib.wasp_emu_run.restype = C.c_long
-    lib.wasp_emu_run.argtypes = [C.c_long] * 5 + [_dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_long]
+    lib.wasp_emu_run.argtypes = [C.c_long] * 5 + [_dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_long] * 5
     return lib
 
 
@@ -51,9 +51,50 @@ def run(wemu, n, u, rhs, v1, v2, K, post, arith, dt, nu, dx, cu=None, rb=16):
     partials = np.zeros(4096)
     cus = None if cu is None else to_split(cu)
     nt = wemu.wasp_emu_run(n, pitch, odd, cp, co, ptr(us), ptr(out), ptr(to_split(rhs)), ptr(to_split(v1)), ptr(to_split(v2)),
-                           ptr(cus), ptr(crhs), ptr(partials), K, post, arith, dt, nu, dx, rb)
+                           ptr(cus), ptr(crhs), ptr(partials), K, post, arith, dt, nu, dx, rb, 0, -1, 0, 0)
     assert 0 < nt <= 4096
     return from_split(out, n), from_split(crhs, n // 2), partials[:nt]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("P", [2, 4])
+def test_row_slabs(wemu, oracle, P):
+    """the same pass on row slabs (own rows + 8 halo rows held, like the sharded solver's windows): every
+    slab is computed from its own window only and the pieces equal the unsharded oracle result"""
+    n, K, HALO = 128, 3, 8
+    u, rhs, v1, v2 = fields(n, 99)
+    cu = np.random.default_rng(3).standard_normal((n // 2 + 1, n // 2 + 1))
+    cu[0, :] = cu[-1, :] = 0; cu[:, 0] = cu[:, -1] = 0
+    dx = 1.0 / n; dt = dx / 10; nu = -4e-4
+    start = u + oracle.prolongation(cu, n // 2)
+    want_u = oracle.gauss_seidel(start.copy(), rhs, n, v1, v2, dt, nu, dx, K)
+    want_c = oracle.restriction(oracle.residual(want_u, rhs, n, v1, v2, dt, nu, dx), n)
+    pitch, odd = layout(n); cp, co = layout(n // 2)
+    S = [to_split(a) for a in (u, rhs, v1, v2)]
+    CU = to_split(cu)
+    got_u = np.full((n + 1, n + 1), np.nan)
+    got_c = np.zeros((n // 2 + 1, n // 2 + 1))
+    per = n // P
+    for r in range(P):
+        own_lo, own_hi = r * per, (r + 1) * per - 1 + (1 if r == P - 1 else 0)
+        mem_lo, mem_hi = max(0, own_lo - HALO), min(n, own_hi + HALO)
+        clo, chi = max(0, (own_lo + 1) // 2 - HALO), min(n // 2, own_hi // 2 + HALO)
+        win = [np.ascontiguousarray(a[mem_lo:mem_hi + 1]) for a in S]
+        cwin = np.ascontiguousarray(CU[clo:chi + 1])
+        out = np.full((mem_hi - mem_lo + 1, pitch), np.nan)
+        crhs = np.zeros((chi - clo + 1, cp))
+        parts = np.zeros(4096)
+        nt = wemu.wasp_emu_run(n, pitch, odd, cp, co, ptr(win[0]), ptr(out), ptr(win[1]), ptr(win[2]), ptr(win[3]), ptr(cwin),
+                               ptr(crhs), ptr(parts), K, 1, 1, dt, nu, dx, 24, own_lo, own_hi, mem_lo, clo)
+        assert nt > 0
+        full = np.full((n + 1, pitch), np.nan); full[mem_lo:mem_hi + 1] = out
+        got_u[own_lo:own_hi + 1] = from_split(full, n)[own_lo:own_hi + 1]
+        cfull = np.zeros((n // 2 + 1, cp)); cfull[clo:chi + 1] = crhs
+        c = from_split(cfull, n // 2)
+        ilo, ihi = (own_lo + 1) // 2, own_hi // 2
+        got_c[ilo:ihi + 1] = c[ilo:ihi + 1]
+    assert np.array_equal(got_u, want_u)
+    assert np.array_equal(got_c[1:-1, 1:-1], want_c[1:-1, 1:-1])
 
 
 @pytest.mark.timeout(600)
