@@ -67,6 +67,8 @@ struct Strip {
     unsigned own[2];                    // owned (stored / summed) nodes per column parity, interior or not
     unsigned oint[2];                   // owned AND interior column
     long b0, b1, R0, R1;                // owned rows, staged rows
+    long ulo, uhi;                      // rows the half-sweeps may update: interior rows strictly inside the staged ones
+    long elo, ehi;                      // rows of the epilogue: owned interior rows
 };
 
 WP_FN Strip make_strip(const Params& p, int strip, int band, int lane)
@@ -95,12 +97,16 @@ WP_FN Strip make_strip(const Params& p, int strip, int band, int lane)
     s.b1 = s.b0 + p.RB - 1 < p.own_hi ? s.b0 + p.RB - 1 : p.own_hi;
     s.R0 = s.b0 - hrow < 0 ? 0 : s.b0 - hrow;          // (a slab holds at least 2K+1 halo rows per side)
     s.R1 = s.b1 + hrow > p.n ? p.n : s.b1 + hrow;
+    s.ulo = s.R0 + 1 > 1 ? s.R0 + 1 : 1;
+    s.uhi = s.R1 - 1 < p.n - 1 ? s.R1 - 1 : p.n - 1;
+    s.elo = s.b0 > 1 ? s.b0 : 1;
+    s.ehi = s.b1 < p.n - 1 ? s.b1 : p.n - 1;
     return s;
 }
 
 WP_FN V2 ld_run(const Params& p, const Strip& s, const double* a, long row, int par)
 {
-    if (!s.live) return V2{0.0, 0.0};
+    if (!s.live) return V2{0.0, 0.0};       // lanes outside the level (first / last strip only)
     return wp_ld2(a + (row - p.row0) * p.pitch + (par ? p.odd : 0) + s.k);
 }
 
@@ -160,7 +166,7 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
     {
         const long e = t - 2 * K - 2;
         constexpr int c = 2 * K + 1;
-        if (p.post != POST_NONE && e >= s.b0 && e <= s.b1 && e >= 1 && e <= p.n - 1) {
+        if (p.post != POST_NONE && e >= s.elo && e <= s.ehi) {
             if (!(p.post == POST_INJECT && (e & 1))) {
                 // even columns (needed by both kinds)
                 double n0, n1, n2;
@@ -204,7 +210,7 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
     for (int q = 0; q < 2 * K; ++q) {
         const long i = t - 1 - q;
         const int a = 1 + q;
-        if (i > s.R0 && i < s.R1 && i >= 1 && i <= p.n - 1) {                 // warp-uniform
+        if (i >= s.ulo && i <= s.uhi) {                                       // warp-uniform
             V2& tgt = PAR ? wO[a] : wE[a];
             const V2 up = PAR ? wO[a + 1] : wE[a + 1], dn = PAR ? wO[a - 1] : wE[a - 1];
             double n0, n1, n2;
