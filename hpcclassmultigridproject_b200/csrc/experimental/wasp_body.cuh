@@ -104,12 +104,6 @@ WP_FN Strip make_strip(const Params& p, int strip, int band, int lane)
     return s;
 }
 
-WP_FN V2 ld_run(const Params& p, const Strip& s, const double* a, long row, int par)
-{
-    if (!s.live) return V2{0.0, 0.0};       // lanes outside the level (first / last strip only)
-    return wp_ld2(a + (row - p.row0) * p.pitch + (par ? p.odd : 0) + s.k);
-}
-
 WP_FN void st_masked(double* q, V2 v, unsigned m)
 {
     if (m == 3u) wp_st2(q, v);
@@ -157,25 +151,43 @@ WP_FN void side(const V2& m, double& n0, double& n1, double& n2)
     n0 = PAR ? m.x : x; n1 = PAR ? m.y : m.x; n2 = PAR ? x : m.y;
 }
 
-// One step of the strip.  W rows of window: index j holds row (t - j) after the new row came in.
-template <int ARITH, int K, int PAR>
-WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2 (&wO)[2 * K + 3], double& acc)
+// per-lane addressing: array bases with the lane's first pair folded in (a lane outside the level
+// -- first / last strip only -- is parked on pair 0: it reads legal memory, and whatever it computes
+// is masked (ok / own are 0) and never reaches a valid node of a live lane), row offsets as 32-bit
+// element counts relative to the arrays' first held row (the launcher checks that they fit)
+struct Lane {
+    const double *u, *rhs, *v1, *v2;
+    double* out;
+    int pitch, odd;
+};
+
+WP_FN V2 ld_at(const double* base, int off) { return wp_ld2(base + off); }
+
+// One step of the strip.  Window index j holds row (t - j) once the new row has come in.
+// ro: element offset of row t.  FULL: every part of the step is active (steady state of a band):
+// no range checks.  Row e = t-2K-2 of the epilogue has the parity of t, so it is even iff PAR == 1.
+// PRE / POSTK: the pass flavour when known at compile time (-1: read p.pre / p.post).
+template <int ARITH, int K, int PAR, bool FULL, int PRE, int POSTK>
+WP_FN void step(const Params& p, const Strip& s, const Lane& ln, long t, int ro, V2 (&wE)[2 * K + 3], V2 (&wO)[2 * K + 3], double& acc)
 {
     constexpr int NW = 2 * K + 3;
+    const int post = POSTK >= 0 ? POSTK : p.post;
+    const bool pre = PRE >= 0 ? (PRE != 0) : (p.pre != 0);
     // ---- epilogue of row e = t-2K-2: indices are still relative to t-1 here (row t-1-j at j)
     {
         const long e = t - 2 * K - 2;
         constexpr int c = 2 * K + 1;
-        if (p.post != POST_NONE && e >= s.elo && e <= s.ehi) {
-            if (!(p.post == POST_INJECT && (e & 1))) {
-                // even columns (needed by both kinds)
+        const int eo = ro - (2 * K + 2) * ln.pitch;
+        if (post != POST_NONE && (FULL || (e >= s.elo && e <= s.ehi))) {
+            if (post == POST_NORM2 || PAR == 1) {
+                // even columns (needed by both kinds; injection: even rows only)
                 double n0, n1, n2;
                 side<0>(wO[c], n0, n1, n2);
-                const V2 f = ld_run(p, s, p.rhs, e, 0), a = ld_run(p, s, p.v1, e, 0), b = ld_run(p, s, p.v2, e, 0);
+                const V2 f = ld_at(ln.rhs, eo), a = ld_at(ln.v1, eo), b = ld_at(ln.v2, eo);
                 const Coef4 c0 = Arith<ARITH>::coef(a.x, b.x, p.st), c1 = Arith<ARITH>::coef(a.y, b.y, p.st);
                 const double r0 = Arith<ARITH>::residual(f.x, wE[c].x, wE[c + 1].x, n0, wE[c - 1].x, n1, c0, p.st);
                 const double r1 = Arith<ARITH>::residual(f.y, wE[c].y, wE[c + 1].y, n1, wE[c - 1].y, n2, c1, p.st);
-                if (p.post == POST_INJECT) {
+                if (post == POST_INJECT) {
                     // coarse node (e/2, kk) for even column 2kk: kk = k is even (coarse even run), k+1 odd
                     double* row = p.crhs + ((e >> 1) - p.crow0) * p.cpitch;
                     if (s.oint[0] & 1u) row[s.k >> 1] = r0;                                   // gs.cpp:283
@@ -185,10 +197,10 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
                     if (s.oint[0] & 2u) acc += r1 * r1;
                 }
             }
-            if (p.post == POST_NORM2) {
+            if (post == POST_NORM2) {
                 double n0, n1, n2;
                 side<1>(wE[c], n0, n1, n2);
-                const V2 f = ld_run(p, s, p.rhs, e, 1), a = ld_run(p, s, p.v1, e, 1), b = ld_run(p, s, p.v2, e, 1);
+                const V2 f = ld_at(ln.rhs, eo + ln.odd), a = ld_at(ln.v1, eo + ln.odd), b = ld_at(ln.v2, eo + ln.odd);
                 const Coef4 c0 = Arith<ARITH>::coef(a.x, b.x, p.st), c1 = Arith<ARITH>::coef(a.y, b.y, p.st);
                 const double r0 = Arith<ARITH>::residual(f.x, wO[c].x, wO[c + 1].x, n0, wO[c - 1].x, n1, c0, p.st);
                 const double r1 = Arith<ARITH>::residual(f.y, wO[c].y, wO[c + 1].y, n1, wO[c - 1].y, n2, c1, p.st);
@@ -200,22 +212,23 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
     // ---- the window moves down one row; row t comes in (+ prolongation and correction)
 #pragma unroll
     for (int j = NW - 1; j >= 1; --j) { wE[j] = wE[j - 1]; wO[j] = wO[j - 1]; }
-    if (t <= s.R1) {
-        if (p.u_in) { wE[0] = ld_run(p, s, p.u_in, t, 0); wO[0] = ld_run(p, s, p.u_in, t, 1); }
+    if (FULL || t <= s.R1) {
+        if (p.u_in) { wE[0] = ld_at(ln.u, ro); wO[0] = ld_at(ln.u, ro + ln.odd); }
         else { wE[0] = V2{0.0, 0.0}; wO[0] = V2{0.0, 0.0}; }
-        if (p.pre) prolong_row(p, s, t, wE[0], wO[0]);
+        if (pre) prolong_row(p, s, t, wE[0], wO[0]);
     }
     // ---- all half-sweeps in order: stage q on row t-1-q = window index 1+q, all on column parity PAR
 #pragma unroll
     for (int q = 0; q < 2 * K; ++q) {
         const long i = t - 1 - q;
         const int a = 1 + q;
-        if (i >= s.ulo && i <= s.uhi) {                                       // warp-uniform
+        if (FULL || (i >= s.ulo && i <= s.uhi)) {                             // warp-uniform
             V2& tgt = PAR ? wO[a] : wE[a];
             const V2 up = PAR ? wO[a + 1] : wE[a + 1], dn = PAR ? wO[a - 1] : wE[a - 1];
             double n0, n1, n2;
             side<PAR>(PAR ? wE[a] : wO[a], n0, n1, n2);
-            const V2 f = ld_run(p, s, p.rhs, i, PAR), va = ld_run(p, s, p.v1, i, PAR), vb = ld_run(p, s, p.v2, i, PAR);
+            const int so = ro - (1 + q) * ln.pitch + (PAR ? ln.odd : 0);
+            const V2 f = ld_at(ln.rhs, so), va = ld_at(ln.v1, so), vb = ld_at(ln.v2, so);
             const Coef4 c0 = Arith<ARITH>::coef(va.x, vb.x, p.st), c1 = Arith<ARITH>::coef(va.y, vb.y, p.st);
             const double o0 = Arith<ARITH>::gs(f.x, up.x, n0, dn.x, n1, c0, p.st);
             const double o1 = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
@@ -226,38 +239,54 @@ WP_FN void step(const Params& p, const Strip& s, long t, V2 (&wE)[2 * K + 3], V2
     // ---- row t-2K-1 (window index 2K+1) is final: store the owned part
     {
         const long f = t - 2 * K - 1;
-        if (f >= s.b0 && f <= s.b1 && (K > 0 || p.pre)) {
-            double* row = p.u_out + (f - p.row0) * p.pitch + s.k;
+        if ((FULL || (f >= s.b0 && f <= s.b1)) && (K > 0 || pre)) {
+            double* row = ln.out + (ro - (2 * K + 1) * ln.pitch);
             if (s.own[0]) st_masked(row, wE[2 * K + 1], s.own[0]);
-            if (s.own[1]) st_masked(row + p.odd, wO[2 * K + 1], s.own[1]);
+            if (s.own[1]) st_masked(row + ln.odd, wO[2 * K + 1], s.own[1]);
         }
     }
 }
 
-template <int ARITH, int K>
+template <int ARITH, int K, int PRE = -1, int POSTK = -1>
 WP_FN void run_strip_k(const Params& p, int strip, int band, int tile)
 {
     const int lane = wp_lane();
     const Strip s = make_strip(p, strip, band, lane);
+    const long ks = s.live ? s.k : 0;
+    Lane ln;
+    ln.u = p.u_in ? p.u_in + ks : nullptr; ln.rhs = p.rhs + ks; ln.v1 = p.v1 + ks; ln.v2 = p.v2 + ks; ln.out = p.u_out + ks;
+    ln.pitch = (int)p.pitch; ln.odd = (int)p.odd;
     V2 wE[2 * K + 3], wO[2 * K + 3];
 #pragma unroll
     for (int j = 0; j < 2 * K + 3; ++j) { wE[j] = V2{0.0, 0.0}; wO[j] = V2{0.0, 0.0}; }
     double acc = 0.0;
-    // steps R0 .. R1+2K+2, two per trip so that the column parity (t-1)&1 is a compile-time constant
-    long t = s.R0;
+    // steps R0 .. R1+2K+2.  Steady state (every stage, the store and the epilogue active, a row to
+    // load): tf0 .. tf1, run without range checks.  The column parity (t-1)&1 picks the code.
     const long tend = s.R1 + 2 * K + 2;
-    if ((t - 1) & 1) { step<ARITH, K, 1>(p, s, t, wE, wO, acc); ++t; }
-    for (; t + 1 <= tend; t += 2) {
-        step<ARITH, K, 0>(p, s, t, wE, wO, acc);
-        step<ARITH, K, 1>(p, s, t + 1, wE, wO, acc);
+    long tf0 = s.ulo + 2 * K, tf1 = s.uhi + 1;
+    if (s.elo + 2 * K + 2 > tf0) tf0 = s.elo + 2 * K + 2;
+    if (s.b0 + 2 * K + 1 > tf0) tf0 = s.b0 + 2 * K + 1;
+    if (s.ehi + 2 * K + 2 < tf1) tf1 = s.ehi + 2 * K + 2;
+    if (s.b1 + 2 * K + 1 < tf1) tf1 = s.b1 + 2 * K + 1;
+    if (s.R1 < tf1) tf1 = s.R1;
+    int ro = (int)((s.R0 - p.row0) * p.pitch);
+    for (long t = s.R0; t <= tend; ++t, ro += ln.pitch) {
+        const bool full = t >= tf0 && t <= tf1;
+        if ((t - 1) & 1) {
+            if (full) step<ARITH, K, 1, true, PRE, POSTK>(p, s, ln, t, ro, wE, wO, acc);
+            else step<ARITH, K, 1, false, PRE, POSTK>(p, s, ln, t, ro, wE, wO, acc);
+        } else {
+            if (full) step<ARITH, K, 0, true, PRE, POSTK>(p, s, ln, t, ro, wE, wO, acc);
+            else step<ARITH, K, 0, false, PRE, POSTK>(p, s, ln, t, ro, wE, wO, acc);
+        }
     }
-    if (t <= tend) step<ARITH, K, 0>(p, s, t, wE, wO, acc);
-    if (p.post == POST_NORM2) {
+    if ((POSTK >= 0 ? POSTK : p.post) == POST_NORM2) {
         const double tot = wp_warp_sum(acc);
         if (lane == 0) p.partials[tile] = tot;
     }
 }
 
+// generic entry: K and the flavour read from the parameters (passes with K < KMAX)
 template <int ARITH>
 WP_FN void run_strip(const Params& p, int tile)
 {
@@ -268,6 +297,13 @@ WP_FN void run_strip(const Params& p, int tile)
         case 2: run_strip_k<ARITH, 2>(p, strip, band, tile); break;
         default: run_strip_k<ARITH, 3>(p, strip, band, tile); break;
     }
+}
+
+// K = KMAX with the flavour fixed at compile time: the passes that matter (one kernel image each)
+template <int ARITH, int PRE, int POSTK>
+WP_FN void run_strip_flavour(const Params& p, int tile)
+{
+    run_strip_k<ARITH, KMAX, PRE, POSTK>(p, tile % p.nstrips, tile / p.nstrips, tile);
 }
 
 // geometry: strips of OWN pairs over pairs 0..nhalf, bands of RB rows over the nrows produced rows

@@ -57,6 +57,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_wasp_pass(const Params p
     run_strip<ARITH>(p, tile);
 }
 
+// K = 3 passes: one image per flavour (prolongation role or not, epilogue kind)
+template <int ARITH, int PRE, int POSTK>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA) k_wasp_pass3(const Params p)
+{
+    const int tile = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (tile >= p.nstrips * p.nbands) return;
+    run_strip_flavour<ARITH, PRE, POSTK>(p, tile);
+}
+
+using WaspKernel = void (*)(const Params);
+template <int ARITH>
+static WaspKernel kernel_of(int K, bool pre, int post)
+{
+    if (K != KMAX) return k_wasp_pass<ARITH>;
+    if (pre) return post == POST_NORM2 ? k_wasp_pass3<ARITH, 1, POST_NORM2> : post == POST_INJECT ? k_wasp_pass3<ARITH, 1, POST_INJECT>
+                                                                                                  : k_wasp_pass3<ARITH, 1, POST_NONE>;
+    return post == POST_NORM2 ? k_wasp_pass3<ARITH, 0, POST_NORM2> : post == POST_INJECT ? k_wasp_pass3<ARITH, 0, POST_INJECT>
+                                                                                          : k_wasp_pass3<ARITH, 0, POST_NONE>;
+}
+
 }  // namespace wasp
 }  // namespace mgb200
 
@@ -96,8 +116,10 @@ int mgb200x_wasp_pass(long n, const double* u_in, double* u_out, const double* r
     const int tiles = p.nstrips * p.nbands;
     const unsigned grid = (unsigned)((tiles + wasp::WARPS_PER_CTA - 1) / wasp::WARPS_PER_CTA);
     cudaStream_t s = (cudaStream_t)stream;
-    if (arith == MGB200_ARITH_EXACT) wasp::k_wasp_pass<MGB200_ARITH_EXACT><<<grid, 32 * wasp::WARPS_PER_CTA, 0, s>>>(p);
-    else wasp::k_wasp_pass<MGB200_ARITH_FAST><<<grid, 32 * wasp::WARPS_PER_CTA, 0, s>>>(p);
+    if ((long)(n + 1) * L.pitch >= (1L << 31)) return fail(MGB200_ERR_INVALID, "wasp_pass: level too large for 32-bit row offsets");
+    const wasp::WaspKernel kern = arith == MGB200_ARITH_EXACT ? wasp::kernel_of<MGB200_ARITH_EXACT>(K, p.pre != 0, post)
+                                                              : wasp::kernel_of<MGB200_ARITH_FAST>(K, p.pre != 0, post);
+    kern<<<grid, 32 * wasp::WARPS_PER_CTA, 0, s>>>(p);
     return check_launch("k_wasp_pass");
 }
 

@@ -99,8 +99,25 @@ long wasp_emu_run(long n, long pitch, long odd, long cpitch, long codd, const do
         for (int l = 0; l < 32; ++l)
             lanes.emplace_back([&, l] {
                 wasp::t_lane = l;
-                if (arith == MGB200_ARITH_EXACT) wasp::run_strip<MGB200_ARITH_EXACT>(p, tile);
-                else wasp::run_strip<MGB200_ARITH_FAST>(p, tile);
+                // K = 3: the compile-time flavours the CUDA dispatcher picks; otherwise the generic entry
+                const bool fl = p.K == wasp::KMAX;
+                if (arith == MGB200_ARITH_EXACT) {
+                    if (!fl) wasp::run_strip<MGB200_ARITH_EXACT>(p, tile);
+                    else if (p.pre && p.post == POST_NORM2) wasp::run_strip_flavour<MGB200_ARITH_EXACT, 1, POST_NORM2>(p, tile);
+                    else if (p.pre && p.post == POST_INJECT) wasp::run_strip_flavour<MGB200_ARITH_EXACT, 1, POST_INJECT>(p, tile);
+                    else if (p.pre) wasp::run_strip_flavour<MGB200_ARITH_EXACT, 1, POST_NONE>(p, tile);
+                    else if (p.post == POST_NORM2) wasp::run_strip_flavour<MGB200_ARITH_EXACT, 0, POST_NORM2>(p, tile);
+                    else if (p.post == POST_INJECT) wasp::run_strip_flavour<MGB200_ARITH_EXACT, 0, POST_INJECT>(p, tile);
+                    else wasp::run_strip_flavour<MGB200_ARITH_EXACT, 0, POST_NONE>(p, tile);
+                } else {
+                    if (!fl) wasp::run_strip<MGB200_ARITH_FAST>(p, tile);
+                    else if (p.pre && p.post == POST_NORM2) wasp::run_strip_flavour<MGB200_ARITH_FAST, 1, POST_NORM2>(p, tile);
+                    else if (p.pre && p.post == POST_INJECT) wasp::run_strip_flavour<MGB200_ARITH_FAST, 1, POST_INJECT>(p, tile);
+                    else if (p.pre) wasp::run_strip_flavour<MGB200_ARITH_FAST, 1, POST_NONE>(p, tile);
+                    else if (p.post == POST_NORM2) wasp::run_strip_flavour<MGB200_ARITH_FAST, 0, POST_NORM2>(p, tile);
+                    else if (p.post == POST_INJECT) wasp::run_strip_flavour<MGB200_ARITH_FAST, 0, POST_INJECT>(p, tile);
+                    else wasp::run_strip_flavour<MGB200_ARITH_FAST, 0, POST_NONE>(p, tile);
+                }
             });
         for (auto& t : lanes) t.join();
     }
