@@ -110,35 +110,46 @@ WP_FN void st_masked(double* q, V2 v, unsigned m)
     else { if (m & 1u) q[0] = v.x; if (m & 2u) q[1] = v.y; }
 }
 
-// coarse value C[I][J] (split layout of the coarse level), 0 outside
-WP_FN double coarse_at(const Params& p, long I, long J)
-{
-    const long nc = p.nhalf;
-    if (I < 0 || I > nc || J < 0 || J > nc) return 0.0;
-    return p.cu[(I - p.crow0) * p.cpitch + (J & 1) * p.codd + (J >> 1)];
-}
+// per-lane addressing: array bases with the lane's first pair folded in (a lane outside the level
+// -- first / last strip only -- is parked on pair 0: it reads legal memory, and whatever it computes
+// is masked (ok / own are 0) and never reaches a valid node of a live lane), row offsets as 32-bit
+// element counts relative to the arrays' first held row (the launcher checks that they fit)
+struct Lane {
+    const double *u, *rhs, *v1, *v2, *cu;
+    double* out;
+    int pitch, odd, cpitch, codd;
+};
 
-// prolongation + correction of the freshly loaded row t (gs.cpp:238-241 + multigrid.cpp:83), interior nodes
-WP_FN void prolong_row(const Params& p, const Strip& s, long t, V2& E, V2& O)
+WP_FN V2 ld_at(const double* base, int off) { return wp_ld2(base + off); }
+
+// prolongation + correction of the freshly loaded row t (gs.cpp:238-241 + multigrid.cpp:83), interior
+// nodes.  The lane's fine columns 2k .. 2k+3 lie between coarse columns k, k+1, k+2 (k even: even run
+// index k/2, odd run index k/2, even run index k/2+1).  No bounds checks: a coarse value beyond the
+// level (slack of the layout) only ever feeds a node that is masked below.
+WP_FN void prolong_row(const Params& p, const Strip& s, const Lane& ln, long t, V2& E, V2& O)
 {
-    if (!s.live || t < 1 || t > p.n - 1) return;
-    const long I = t >> 1, k = s.k;
-    const double a0 = coarse_at(p, I, k), a1 = coarse_at(p, I, k + 1), a2 = coarse_at(p, I, k + 2);
+    if (t < 1 || t > p.n - 1) return;
+    const int cro = (int)(((t >> 1) - p.crow0) * ln.cpitch);
+    const long k = s.k;
+    const double a0 = ln.cu[cro], a1 = ln.cu[cro + ln.codd], a2 = ln.cu[cro + 1];
     double e0, e1, o0, o1;
     if ((t & 1) == 0) {
         e0 = a0; e1 = a1;                                                                   // gs.cpp:238
         o0 = __dmul_rn(__dadd_rn(a0, a1), 0.5); o1 = __dmul_rn(__dadd_rn(a1, a2), 0.5);     // gs.cpp:240
     } else {
-        const double b0 = coarse_at(p, I + 1, k), b1 = coarse_at(p, I + 1, k + 1), b2 = coarse_at(p, I + 1, k + 2);
+        const int c1 = cro + ln.cpitch;
+        const double b0 = ln.cu[c1], b1 = ln.cu[c1 + ln.codd], b2 = ln.cu[c1 + 1];
         e0 = __dmul_rn(__dadd_rn(a0, b0), 0.5); e1 = __dmul_rn(__dadd_rn(a1, b1), 0.5);     // gs.cpp:239
         o0 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a0, b0), a1), b1), 0.25);              // gs.cpp:241
         o1 = __dmul_rn(__dadd_rn(__dadd_rn(__dadd_rn(a1, b1), a2), b2), 0.25);
     }
     // interior columns only: even column 2kk for 1 <= kk <= nhalf-1, odd column 2kk+1 for kk <= nhalf-1
-    if (k >= 1 && k <= p.nhalf - 1) E.x = __dadd_rn(E.x, e0);
-    if (k + 1 >= 1 && k + 1 <= p.nhalf - 1) E.y = __dadd_rn(E.y, e1);
-    if (k <= p.nhalf - 1) O.x = __dadd_rn(O.x, o0);
-    if (k + 1 <= p.nhalf - 1) O.y = __dadd_rn(O.y, o1);
+    if (s.live) {
+        if (k >= 1 && k <= p.nhalf - 1) E.x = __dadd_rn(E.x, e0);
+        if (k + 1 <= p.nhalf - 1) E.y = __dadd_rn(E.y, e1);
+        if (k <= p.nhalf - 1) O.x = __dadd_rn(O.x, o0);
+        if (k + 1 <= p.nhalf - 1) O.y = __dadd_rn(O.y, o1);
+    }
 }
 
 // operands of the nodes of column parity PAR in a row: `m` is the other run of the same row
@@ -150,18 +161,6 @@ WP_FN void side(const V2& m, double& n0, double& n1, double& n2)
     const double x = PAR ? wp_shfl_down(m.x) : wp_shfl_up(m.y);
     n0 = PAR ? m.x : x; n1 = PAR ? m.y : m.x; n2 = PAR ? x : m.y;
 }
-
-// per-lane addressing: array bases with the lane's first pair folded in (a lane outside the level
-// -- first / last strip only -- is parked on pair 0: it reads legal memory, and whatever it computes
-// is masked (ok / own are 0) and never reaches a valid node of a live lane), row offsets as 32-bit
-// element counts relative to the arrays' first held row (the launcher checks that they fit)
-struct Lane {
-    const double *u, *rhs, *v1, *v2;
-    double* out;
-    int pitch, odd;
-};
-
-WP_FN V2 ld_at(const double* base, int off) { return wp_ld2(base + off); }
 
 // One step of the strip.  Window index j holds row (t - j) once the new row has come in.
 // ro: element offset of row t.  FULL: every part of the step is active (steady state of a band):
@@ -179,8 +178,11 @@ WP_FN void step(const Params& p, const Strip& s, const Lane& ln, long t, int ro,
         constexpr int c = 2 * K + 1;
         const int eo = ro - (2 * K + 2) * ln.pitch;
         if (post != POST_NONE && (FULL || (e >= s.elo && e <= s.ehi))) {
-            if (post == POST_NORM2 || PAR == 1) {
-                // even columns (needed by both kinds; injection: even rows only)
+            // Sum of squares after smoothing (K > 0): the last half-sweep's colour ((i+j) odd) is summed
+            // by the last stage itself, the epilogue visits the other colour only: the even columns of an
+            // even row (PAR == 1), the odd columns of an odd row.  Injection: even columns of even rows.
+            if ((post == POST_NORM2 && K == 0) || PAR == 1) {
+                // even columns
                 double n0, n1, n2;
                 side<0>(wO[c], n0, n1, n2);
                 const V2 f = ld_at(ln.rhs, eo), a = ld_at(ln.v1, eo), b = ld_at(ln.v2, eo);
@@ -197,7 +199,7 @@ WP_FN void step(const Params& p, const Strip& s, const Lane& ln, long t, int ro,
                     if (s.oint[0] & 2u) acc += r1 * r1;
                 }
             }
-            if (post == POST_NORM2) {
+            if (post == POST_NORM2 && (K == 0 || PAR == 0)) {
                 double n0, n1, n2;
                 side<1>(wE[c], n0, n1, n2);
                 const V2 f = ld_at(ln.rhs, eo + ln.odd), a = ld_at(ln.v1, eo + ln.odd), b = ld_at(ln.v2, eo + ln.odd);
@@ -215,7 +217,7 @@ WP_FN void step(const Params& p, const Strip& s, const Lane& ln, long t, int ro,
     if (FULL || t <= s.R1) {
         if (p.u_in) { wE[0] = ld_at(ln.u, ro); wO[0] = ld_at(ln.u, ro + ln.odd); }
         else { wE[0] = V2{0.0, 0.0}; wO[0] = V2{0.0, 0.0}; }
-        if (pre) prolong_row(p, s, t, wE[0], wO[0]);
+        if (pre) prolong_row(p, s, ln, t, wE[0], wO[0]);
     }
     // ---- all half-sweeps in order: stage q on row t-1-q = window index 1+q, all on column parity PAR
 #pragma unroll
@@ -234,6 +236,13 @@ WP_FN void step(const Params& p, const Strip& s, const Lane& ln, long t, int ro,
             const double o1 = Arith<ARITH>::gs(f.y, up.y, n1, dn.y, n2, c1, p.st);
             if (s.ok[PAR] & 1u) tgt.x = o0;
             if (s.ok[PAR] & 2u) tgt.y = o1;
+            if (q == 2 * K - 1 && post == POST_NORM2 && i >= s.elo && i <= s.ehi) {
+                // residual of the nodes just updated: all operands are in registers (owned nodes are never masked)
+                const double r0 = Arith<ARITH>::residual(f.x, o0, up.x, n0, dn.x, n1, c0, p.st);
+                const double r1 = Arith<ARITH>::residual(f.y, o1, up.y, n1, dn.y, n2, c1, p.st);
+                if (s.oint[PAR] & 1u) acc += r0 * r0;
+                if (s.oint[PAR] & 2u) acc += r1 * r1;
+            }
         }
     }
     // ---- row t-2K-1 (window index 2K+1) is final: store the owned part
@@ -255,7 +264,8 @@ WP_FN void run_strip_k(const Params& p, int strip, int band, int tile)
     const long ks = s.live ? s.k : 0;
     Lane ln;
     ln.u = p.u_in ? p.u_in + ks : nullptr; ln.rhs = p.rhs + ks; ln.v1 = p.v1 + ks; ln.v2 = p.v2 + ks; ln.out = p.u_out + ks;
-    ln.pitch = (int)p.pitch; ln.odd = (int)p.odd;
+    ln.cu = p.cu ? p.cu + (ks >> 1) : nullptr;
+    ln.pitch = (int)p.pitch; ln.odd = (int)p.odd; ln.cpitch = (int)p.cpitch; ln.codd = (int)p.codd;
     V2 wE[2 * K + 3], wO[2 * K + 3];
 #pragma unroll
     for (int j = 0; j < 2 * K + 3; ++j) { wE[j] = V2{0.0, 0.0}; wO[j] = V2{0.0, 0.0}; }
