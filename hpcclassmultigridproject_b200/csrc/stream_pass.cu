@@ -324,8 +324,21 @@ int stream_pass_init()
     return MGB200_OK;
 }
 
+// A/B switch while both implementations exist: MGB200_PASS=barrier selects the barrier-per-row kernel
+static bool use_syst()
+{
+    static const bool v = [] { const char* e = getenv("MGB200_PASS"); return !(e && std::string(e) == "barrier"); }();
+    return v;
+}
+
 long stream_pass_tiles(long n, long nrows, int iters)
 {
+    if (use_syst() && iters >= 1) return syst_pass_tiles(n, nrows, iters);
+    if (use_syst() && iters < 0) {
+        long m = syst_pass_tiles(n, nrows, -1);
+        const Plan& pl = plan_for(n, nrows, 0);
+        return std::max(m, (long)pl.nstrips * pl.nbands);
+    }
     if (iters >= 0) {
         const Plan& pl = plan_for(n, nrows, iters > KMAX ? KMAX : iters);
         return (long)pl.nstrips * pl.nbands;
@@ -342,6 +355,7 @@ static int build_params(const StreamPassArgs& a, Params& p, unsigned& grid, size
 
 int stream_pass(const StreamPassArgs& a, cudaStream_t s)
 {
+    if (use_syst() && a.iters >= 1) return syst_pass(a, s);
     // The kernel parameter block (five encoded tensor maps, the tile plan, the row window) depends
     // only on the argument record: a solver issues the same few dozen passes every cycle, so blocks
     // are built once and looked up by the raw bytes of the arguments.

@@ -46,4 +46,9 @@ long stream_pass_tiles(long n, long nrows, int iters);
 int stream_pass_init();
 int stream_pass(const StreamPassArgs& a, cudaStream_t s);
 
+// the systolic implementation of the same pass (syst_pass.cu): iters >= 1 only
+int syst_pass_init();
+long syst_pass_tiles(long n, long nrows, int iters);
+int syst_pass(const StreamPassArgs& a, cudaStream_t s);
+
 }  // namespace mgb200

@@ -19,6 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.oracle import Oracle, Towers  # noqa: E402
+from hpcclassmultigridproject_b200.digest import combine, slab_digests  # noqa: E402  (hashlib only, no library load)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 CFG = {
@@ -28,6 +29,9 @@ CFG = {
     "large_n8192": dict(n=8192, nu=-4e-4, vscale=1.0, tol=1e-10),
     # configs[2]: the headline size
     "large_c3_n16384": dict(n=16384, nu=-4e-4, vscale=1.0, tol=1e-10),
+    # configs[2] at the tolerance bench.py runs (tol = 1e-6: 3 cycles); carries the slab digests of the
+    # whole final field (hpcclassmultigridproject_b200/digest.py) for the bench line's parity block
+    "large_c3_n16384_tol1e-6": dict(n=16384, nu=-4e-4, vscale=1.0, tol=1e-6),
     # configs[3]: advection-dominated
     "large_c4_n16384": dict(n=16384, nu=-1e-6, vscale=1.0, tol=1e-10),
 }
@@ -47,6 +51,10 @@ def run(tag, n, nu, vscale, tol, threads=8):
     out = dict(n=n, nu=nu, vscale=vscale, tol=tol, dx=dx, dt=dt, steps=1, cycles=it, hist=h,
                norm_uT=float(np.sqrt(np.sum(uT * uT))), mid=uT[n // 2, n // 2],
                sample=uT[::st, ::st].copy(), stride=st)
+    dense = np.ascontiguousarray(uT)
+    dig = slab_digests(dense, n)
+    out["slab_sha256"] = np.array([dig[g].hex() for g in sorted(dig)])
+    out["u_sha256"] = combine(dig)
     np.savez_compressed(os.path.join(OUT, tag + ".npz"), **out)
     print(tag, "cycles", it, "hist", h / h[0], "norm", out["norm_uT"], "mid", out["mid"],
           "%.1fs" % (time.time() - t0), flush=True)
