@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -35,7 +36,6 @@ sys.path.insert(0, ROOT)
 
 N_FULL = 16384
 NU, VSCALE, TOL = -4e-4, 1.0, 1e-6
-METRIC = "V-cycle ms at N=16384^2 (fine-grid V-cycle incl. convergence check)"
 W_REF_BYTES_PER_NODE = 475.0          # reference pass structure, one pass per operator
 
 
@@ -104,18 +104,25 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the compiled reference (or the oracle port) on a bounded sample
-def cpu_vcycle_ms(steps, warmup, threads=None):
+def cpu_vcycle_ms(n_target, steps, warmup, threads=None, budget_s=240.0):
+    """ms per V-cycle (+ convergence check) of the reference CPU implementation at n_target.  The reference's
+    towers take ~145 B per fine node (39 GB at N=16384; multigrid.cpp:138-162): the true size is run when the
+    host has the memory, otherwise the largest size that fits, scaled by the node-count
+    ratio and FLAGGED as such.  Returns (ms, kind, threads, sample text, extra dict)."""
     import numpy as np
     import psutil
     from oracle.oracle import Oracle, OracleSolver, Towers, ref_available
     threads = threads or os.cpu_count() or 1
     free_gb = psutil.virtual_memory().available / 2**30
-    n = 8192 if free_gb > 24 else 4096
-    scale = (N_FULL + 1) ** 2 / float((n + 1) ** 2)
+    n = n_target
+    while n > 256 and (145.0 * (n + 1) ** 2 / 2**30 > 0.8 * free_gb or n > 32768):      # the reference's int indices stop at 32768
+        n //= 2
+    scale = (n_target + 1) ** 2 / float((n + 1) ** 2)
     dx = 1.0 / n; dt = dx / 10
     o = Oracle()
     u0, v1, v2 = o.initial_conditions(n, VSCALE)
     times = []
+    t_start = time.perf_counter()
     if ref_available("O3"):
         kind = "reference"
         tw = Towers(Oracle("O3"), n, u0, v1, v2, NU, dt, dx, TOL, 1)
@@ -126,6 +133,8 @@ def cpu_vcycle_ms(steps, warmup, threads=None):
             tw.cycle_and_norm(threads)
             if k >= warmup:
                 times.append(time.perf_counter() - t)
+            if len(times) >= 2 and time.perf_counter() - t_start > budget_s:           # bounded sample
+                break
     else:
         kind, threads = "port", 1
         s = OracleSolver(n, u0, v1, v2, NU, dt, dx, TOL, 1)
@@ -135,33 +144,106 @@ def cpu_vcycle_ms(steps, warmup, threads=None):
             s.cycle(); s.residual_norm()
             if k >= warmup:
                 times.append(time.perf_counter() - t)
+            if len(times) >= 2 and time.perf_counter() - t_start > budget_s:
+                break
     ms = 1e3 * float(np.mean(times)) * scale
-    sample = (f"{steps} V-cycle(s)+check at N={n} after {warmup} warm-up, mean x{scale:.3f} "
-              f"(node count ratio to N={N_FULL}); {'gs.cpp+multigrid.cpp -O3, OpenMP tasks' if kind == 'reference' else 'oracle/mg_oracle.c -O2, serial'}")
-    return ms, kind, threads, sample
+    impl = "gs.cpp+multigrid.cpp -O3, OpenMP tasks" if kind == "reference" else "oracle/mg_oracle.c -O2, serial"
+    sample = (f"{len(times)} V-cycle(s)+check at N={n} after {warmup} warm-up"
+              + (f", mean x{scale:.3f} (node count ratio to N={n_target}: host RAM {free_gb:.0f} GB < 145 B/node)" if n != n_target else "")
+              + f"; {impl}")
+    extra = {"measured_N": n, "scaled": n != n_target, "scale_factor": scale, "cycles_timed": len(times)}
+    return ms, kind, threads, sample, extra
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    ms, kind, cores, sample = cpu_vcycle_ms(max(1, args.steps), max(0, min(args.warmup, 2)))
+    n = args.n
+    ms, kind, cores, sample, extra = cpu_vcycle_ms(n, max(1, args.steps), max(0, min(args.warmup, 2)))
     line = {
-        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(n), "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference initial conditions, multigrid.cpp:206-233)",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample},
+        "config": workload_config(n, args.gpus),
+        "cpu_baseline": dict({"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample}, **extra),
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "effective_GBps_Wref": W_REF_BYTES_PER_NODE * (N_FULL + 1) ** 2 / (ms * 1e-3) / 1e9,
+        "effective_GBps_Wref": W_REF_BYTES_PER_NODE * (n + 1) ** 2 / (ms * 1e-3) / 1e9,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(gpus):
-    return {"workload": f"C3: N={N_FULL}^2 advection-diffusion Crank-Nicolson step, nu={NU}, vscale={VSCALE}, "
+def metric_name(n):
+    return f"V-cycle ms at N={n}^2 (fine-grid V-cycle incl. convergence check)"
+
+
+def workload_config(n, gpus):
+    """the same dict for both arms (own and reference): BASELINE.json configs[2] ("C3") at the default size,
+    configs[4] ("C5") at N=65536, otherwise just the size"""
+    tag = {16384: "C3: ", 65536: "C5: "}.get(n, "")
+    field_gb = (n + 1) ** 2 * 8 / 1e9
+    return {"workload": f"{tag}N={n}^2 advection-diffusion Crank-Nicolson step, nu={NU}, vscale={VSCALE}, "
                         f"tol={TOL}, V-cycle (3 pre + 3 post RB-GS), {gpus} GPU(s)",
-            "N": N_FULL, "nu": NU, "vscale": VSCALE, "tol": TOL, "shape": 1, "levels": 10,
-            "l2_policy": "inputs (2.1 GB per field) exceed the 126 MB L2; no flush needed"}
+            "N": n, "nu": NU, "vscale": VSCALE, "tol": TOL, "shape": 1, "levels": int(math.log2(n)) - 4,
+            "l2_policy": (f"inputs ({field_gb:.2g} GB per field) exceed the 126 MB L2; no flush needed" if field_gb > 0.3 else
+                          f"inputs ({field_gb:.2g} GB per field) are comparable to the 126 MB L2: a 256 MB buffer is "
+                          "rewritten between timed steps")}
+
+
+# ---------------------------------------------------------------------------------------------
+def parity_block(mg, s, n, rank, world, dist, arith_name):
+    """Parity evidence for the configuration that was just timed: from FRESH reference initial conditions run one
+    implicit time step to tol and describe the result -- cycle count, ||uT||_2, uT[N/2,N/2], a 129 x 129 strided
+    sample, and the rank-count-independent field digest (hpcclassmultigridproject_b200/digest.py) -- then compare it
+    with the fixture the compiled reference produced for this configuration (tests/golden/make_golden_large.py).
+    Sharded ranks describe their own rows; rank 0 stitches.  Returns (dict, ok)."""
+    import numpy as np
+    from hpcclassmultigridproject_b200 import digest
+    s.set_fields_reference_ic(VSCALE)
+    info = s.timestep(1)[0]
+    u = s.get_u_host()                                  # a slab rank fills its own rows, the rest stays NaN
+    sl = s.slab(0)
+    lo, hi = (sl["own_lo"], sl["own_hi"]) if world > 1 else (0, n)
+    st = max(1, n // 128)
+    rows = [i for i in range(0, n + 1, st) if lo <= i <= hi]
+    mine = {
+        "digests": digest.slab_digests(u, n, lo, hi) if n % digest.NSLAB == 0 else {},
+        "sumsq": float(np.sum(u[lo:hi + 1] * u[lo:hi + 1])),
+        "mid": float(u[n // 2, n // 2]) if lo <= n // 2 <= hi else None,
+        "sample_rows": rows, "sample": u[rows, ::st].copy(),
+    }
+    del u
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None, True
+    dig = {}
+    for q in parts:
+        dig.update(q["digests"])
+    sample = np.concatenate([q["sample"] for q in parts], axis=0)
+    assert [i for q in parts for i in q["sample_rows"]] == list(range(0, n + 1, st))
+    norm = math.sqrt(math.fsum(q["sumsq"] for q in parts))
+    mid = [q["mid"] for q in parts if q["mid"] is not None][0]
+    out = {"cycles": int(info.cycles), "converged": bool(info.converged), "res_history": [float(x) for x in info.history()],
+           "norm_uT": norm, "mid": mid, "arith": arith_name,
+           "u_sha256": digest.combine(dig) if len(dig) == digest.NSLAB else None,
+           "digest": "sha256 over the sha256 of 8 fixed row slabs (same value for any rank count)"}
+    ok = True
+    fx = os.path.join(ROOT, "tests", "golden", f"large_c3_n{n}_tol1e-6.npz")
+    if os.path.exists(fx) and (NU, VSCALE, TOL) == (-4e-4, 1.0, 1e-6):
+        g = np.load(fx)
+        rel = float(np.linalg.norm(sample - g["sample"]) / np.linalg.norm(g["sample"]))
+        ref = {"fixture": os.path.relpath(fx, ROOT), "cycles": int(g["cycles"]), "norm_uT": float(g["norm_uT"]), "mid": float(g["mid"]),
+               "u_sha256_reference": str(g["u_sha256"]), "sample_rel_l2": rel,
+               "norm_rel_err": abs(norm - float(g["norm_uT"])) / float(g["norm_uT"]),
+               "mid_rel_err": abs(mid - float(g["mid"])) / abs(float(g["mid"])), "bar": 1e-10}
+        ok = (out["cycles"] == ref["cycles"] and rel <= 1e-10 and ref["norm_rel_err"] <= 1e-10 and ref["mid_rel_err"] <= 1e-10)
+        ref["ok"] = ok
+        out["reference"] = ref
+    else:
+        out["reference"] = None         # no compiled-reference fixture for this size (the reference stops at N=32768)
+    return out, ok
 
 
 # ---------------------------------------------------------------------------------------------
@@ -248,6 +330,7 @@ def run_own(args, rank, world):
             traffic = None
     cycle_bytes = s.cycle_bytes
     slab = s.slab(0)
+    parity, parity_ok = (None, True) if args.no_parity else parity_block(mg, s, n, rank, world, dist, args.arith)
     if world == 1:
         s.close()
 
@@ -313,16 +396,18 @@ def run_own(args, rank, world):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        ms, kind, cores, sample = cpu_vcycle_ms(2, 1)
-        cpu = {"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample}
+        ms, kind, cores, sample, extra = cpu_vcycle_ms(n, 2, 1, budget_s=60.0)
+        cpu = dict({"value": ms, "unit": "ms", "cores": cores, "kind": kind, "sample": sample}, **extra)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": ms_cycle, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(n), "value": ms_cycle, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (reference initial conditions, multigrid.cpp:206-233, generated on device)",
-            "config": dict(workload_config(world), N=n, plan=args.plan, arith=args.arith,
-                           step="one implicit time step = compute_rhs + V-cycles to tol; value = ms / V-cycles"),
+            "config": workload_config(n, world),
+            "impl_config": {"plan": args.plan, "arith": args.arith,
+                            "step": "one implicit time step = compute_rhs + V-cycles to tol; value = ms / V-cycles"},
+            "parity": parity,
             "cycles_per_step": cycles / args.steps, "vcycles_timed": cycles, "vcycle_only_ms": vc,
             "effective_GBps_Wref": W_REF_BYTES_PER_NODE * m0 / (ms_cycle * 1e-3) / 1e9,
             "plan_GBps": cycle_bytes / (ms_cycle * 1e-3) / 1e9, "plan_bytes_per_cycle": cycle_bytes,
@@ -337,6 +422,9 @@ def run_own(args, rank, world):
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+    if rank == 0 and not parity_ok:
+        print("bench.py: PARITY MISMATCH against " + str(parity["reference"]), file=sys.stderr, flush=True)
+        sys.exit(3)
 
 
 def main():
@@ -350,6 +438,7 @@ def main():
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -2,7 +2,6 @@
 // natural layout (element (i,j) at p[i*ld+j]).  They replace the gs.h / gscu.h operators one for
 // one; see include/mgb200.h for the file:line of each reference interface.
 #include <cmath>
-#include <mutex>
 
 #include "ops_basic.cuh"
 
@@ -10,24 +9,19 @@ using namespace mgb200;
 
 namespace {
 
-// grow-only device workspace for block partial sums (+1 slot for the reduced value)
-struct Workspace {
-    std::mutex mu;
+// scratch for block partial sums (+1 slot for the reduced value): allocated and released in stream order on
+// the caller's stream (cudaMallocAsync), so concurrent calls on different streams or devices never share it
+struct Scratch {
     double* buf = nullptr;
-    long cap = 0;
-    int get(long need, double** out)
+    cudaStream_t s;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    int get(long need)
     {
-        if (need > cap) {
-            if (buf) cudaFree(buf);
-            buf = nullptr; cap = 0;
-            MGB_CUDA(cudaMalloc(&buf, (size_t)need * sizeof(double)));
-            cap = need;
-        }
-        *out = buf;
+        MGB_CUDA(cudaMallocAsync(&buf, (size_t)need * sizeof(double), s));
         return MGB200_OK;
     }
+    ~Scratch() { if (buf) cudaFreeAsync(buf, s); }
 };
-Workspace g_ws;
 
 inline bool bad_grid(long n, long ld) { return n < 2 || ld < n + 1; }
 
@@ -59,10 +53,10 @@ int mgb200_residual(double* res, const double* u, const double* rhs, long n, lon
 int mgb200_norm2_async(const double* a, long n, long ld, double* out_dev, void* stream)
 {
     if (!a || !out_dev || bad_grid(n, ld)) return fail(MGB200_ERR_INVALID, "norm2: bad argument");
-    std::lock_guard<std::mutex> lock(g_ws.mu);
     const long cnt = residual_partials_count(n);
-    double* ws = nullptr;
-    MGB_TRY(g_ws.get(cnt + 1, &ws));
+    Scratch sc((cudaStream_t)stream);
+    MGB_TRY(sc.get(cnt + 1));
+    double* ws = sc.buf;
     MGB_TRY(launch_square_partials(a, n, natural_layout(ld), ws, (cudaStream_t)stream));
     return launch_reduce_partials(ws, cnt, out_dev, (cudaStream_t)stream);
 }
@@ -70,10 +64,10 @@ int mgb200_norm2_async(const double* a, long n, long ld, double* out_dev, void* 
 int mgb200_compute_norm(const double* a, long n, long ld, double* out_host, void* stream)
 {
     if (!a || !out_host || bad_grid(n, ld)) return fail(MGB200_ERR_INVALID, "compute_norm: bad argument");
-    std::lock_guard<std::mutex> lock(g_ws.mu);
     const long cnt = residual_partials_count(n);
-    double* ws = nullptr;
-    MGB_TRY(g_ws.get(cnt + 1, &ws));
+    Scratch sc((cudaStream_t)stream);
+    MGB_TRY(sc.get(cnt + 1));
+    double* ws = sc.buf;
     MGB_TRY(launch_square_partials(a, n, natural_layout(ld), ws, (cudaStream_t)stream));
     MGB_TRY(launch_reduce_partials(ws, cnt, ws + cnt, (cudaStream_t)stream));
     double h = 0.0;
@@ -88,10 +82,10 @@ int mgb200_residual_norm2_async(double* res, const double* u, const double* rhs,
                                 void* stream)
 {
     if (!u || !rhs || !v1 || !v2 || !out_dev || bad_grid(n, ld)) return fail(MGB200_ERR_INVALID, "residual_norm2: bad argument");
-    std::lock_guard<std::mutex> lock(g_ws.mu);
     const long cnt = residual_partials_count(n);
-    double* ws = nullptr;
-    MGB_TRY(g_ws.get(cnt + 1, &ws));
+    Scratch sc((cudaStream_t)stream);
+    MGB_TRY(sc.get(cnt + 1));
+    double* ws = sc.buf;
     MGB_TRY(launch_residual(res, u, rhs, v1, v2, n, natural_layout(ld), make_stencil(dt, nu, dx), arith, ws,
                             (cudaStream_t)stream));
     return launch_reduce_partials(ws, cnt, out_dev, (cudaStream_t)stream);

@@ -45,6 +45,13 @@ static inline int check_launch(const char* what)
     return MGB200_OK;
 }
 
+// end-of-solve diagnostics shared by the drivers: the reference's only failure report is the warning of
+// multigrid.cpp:117-119 (which, by an off-by-one, fires on convergence in exactly MAX_CYCLE-1 cycles and not
+// on hitting MAX_CYCLE); here the warning goes to stderr when the loop ended WITHOUT meeting the tolerance,
+// and a non-finite residual norm (the reference then just leaves its loop: NaN > tol is false) is named.
+// Returns false in those cases.  MGB200_QUIET=1 silences the text.
+bool report_solve(int cycles, int max_cycle, double res0, double res, double tol);
+
 static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------------------------

@@ -277,6 +277,12 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "options.restriction: 0 (injection) or 1 (full weighting, UNFUSED plan only)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
         return fail(MGB200_ERR_INVALID, "the sharded solver supports the fused plan with reference-compatible towers only");
+    // niter == 0 (no smoothing at all: multigrid.cpp:69-72 and :85-88 become empty loops) leaves nothing to fuse:
+    // the streaming pass is defined for 1..3 iterations, so such a solver runs the one-operator plan
+    if (opt.niter == 0) {
+        if (P > 1) return fail(MGB200_ERR_INVALID, "niter == 0 is not supported by the sharded solver");
+        opt.plan = MGB200_PLAN_UNFUSED;
+    }
     // the sharded cycle (kernels + peer-memory transfers, or NCCL groups as the fallback) is captured like the
     // single-GPU one; MGB200_SHARDED_GRAPH=0 issues everything directly on the stream instead
     if (P > 1) { const char* e = getenv("MGB200_SHARDED_GRAPH"); if (e && atoi(e) == 0) opt.use_graph = 0; }
@@ -883,6 +889,21 @@ int mgb200_solver::form_rhs(double* res0_out, bool sync)
     return MGB200_OK;
 }
 
+namespace mgb200 {
+bool report_solve(int cycles, int max_cycle, double res0, double res, double tol)
+{
+    const bool finite = std::isfinite(res) && std::isfinite(res0);
+    const bool ok = finite && (res / res0 <= tol || res0 == 0.0);
+    if (ok) return true;
+    static const bool quiet = [] { const char* e = getenv("MGB200_QUIET"); return e && atoi(e) != 0; }();
+    if (!quiet) {
+        if (!finite) fprintf(stderr, "mgb200: residual norm is not finite after %d cycle(s) (res0 = %g, res = %g): the iteration diverged\n", cycles, res0, res);
+        else fprintf(stderr, "multigrid did not converge in %d cycles (res/res0 = %.3e > tol = %.3e)\n", max_cycle, res / res0, tol);   // multigrid.cpp:118
+    }
+    return false;
+}
+}  // namespace mgb200
+
 // mg_outer (multigrid.cpp:97-120)
 int mgb200_solver::solve(mgb200_solve_info* info)
 {
@@ -908,6 +929,7 @@ int mgb200_solver::solve(mgb200_solve_info* info)
             for (int k = 0; k <= it; ++k) info->hist[k] = h_loop->hist[k];
             info->cycles = it; info->res0 = res0; info->res = res; info->converged = (res / res0 <= tol) ? 1 : 0;
         }
+        if (rank == 0) report_solve(it, opt.max_cycle, res0, res, tol);
         return MGB200_OK;
     }
     if (!res0_on_host) {
@@ -924,6 +946,7 @@ int mgb200_solver::solve(mgb200_solve_info* info)
         if (info) info->hist[it + 1] = r;
     }
     if (info) { info->cycles = it; info->res0 = r0; info->res = r; info->converged = (r / r0 <= tol) ? 1 : 0; }
+    if (rank == 0) report_solve(it, opt.max_cycle, r0, r, tol);
     return MGB200_OK;
 }
 
@@ -973,6 +996,7 @@ int mgb200_solver::timestep(int nsteps, mgb200_solve_info* infos)
             for (int c = 0; c <= it; ++c) info.hist[c] = ls.hist[c];
             info.cycles = it; info.res0 = res0; info.res = res; info.converged = (res / res0 <= tol) ? 1 : 0;
         }
+        if (rank == 0) report_solve(it, opt.max_cycle, res0, res, tol);
     }
     return MGB200_OK;
 }

@@ -69,15 +69,26 @@ __device__ __forceinline__ void mbar_wait(unsigned a, unsigned parity)
 
 SY_FN void sy_full_wait(const Smem& sm, int g, unsigned parity) { mbar_wait(sm.base32 + sm.full_off + 8u * g, parity); }
 
-SY_FN void sy_pb_arrive(const Smem& sm, int warp, int slot)
+SY_FN void sy_prog_publish(const Smem& sm, int warp, unsigned steps_done)
 {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(sm.base32 + sm.pb_off + 8u * (unsigned)(warp * PBSLOTS + slot))
-                 : "memory");
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(sm.base32 + sm.pb_off + 4u * (unsigned)warp), "r"(steps_done) : "memory");
 }
 
-SY_FN void sy_pb_wait(const Smem& sm, int warp, int slot, unsigned parity)
+SY_FN Prog2 sy_prog_peek(const Smem& sm, int stage)
 {
-    mbar_wait(sm.base32 + sm.pb_off + 8u * (unsigned)(warp * PBSLOTS + slot), parity);
+    Prog2 v;
+    asm volatile("ld.acquire.cta.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.h0), "=r"(v.h1) : "r"(sm.base32 + sm.pb_off + 8u * (unsigned)stage) : "memory");
+    return v;
+}
+
+#ifndef MGB200_SY_BACKOFF_NS
+#define MGB200_SY_BACKOFF_NS 0
+#endif
+SY_FN void sy_backoff()
+{
+#if MGB200_SY_BACKOFF_NS > 0
+    __nanosleep(MGB200_SY_BACKOFF_NS);
+#endif
 }
 
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes)
@@ -137,8 +148,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_syst_pass(const __grid_constant_
     // the producer's operands live in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    for (int b = threadIdx.x; b < NGROUP + NSTAGE * PBSLOTS; b += THREADS)
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm.base32 + sm.full_off + 8u * b) : "memory");
+    if (threadIdx.x < NGROUP)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm.base32 + sm.full_off + 8u * threadIdx.x) : "memory");
+    if (threadIdx.x < NSTAGE) *reinterpret_cast<volatile unsigned*>(smem_raw + sm.pb_off + 4u * threadIdx.x) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sy_fence_async();
     __syncthreads();

@@ -13,8 +13,9 @@
 // behind stage s-1, updating the ring in place; finished rows leave through bulk stores.
 //
 // What is different from a barrier-per-row pipeline: the warps are coupled ONLY by the data
-// dependencies of the half-sweeps.  Every stage warp publishes "step k done" on its own ring of
-// mbarriers and a warp waits for exactly the warps whose results it reads:
+// dependencies of the half-sweeps.  Every stage warp publishes the number of steps it has completed in
+// a shared-memory counter (store-release after its row is written) and a warp waits (load-acquire,
+// one 8-byte load for both warps of a stage) for exactly the warps whose results it reads:
 //
 //     stage s, step k   needs   stage s-1 (both column halves), step k-1          [row below + strip-half edge]
 //     stage 0           needs   the TMA group of its lower row                     [full barriers]
@@ -22,21 +23,21 @@
 //
 // The reverse (write-after-read) hazards are implied by these: stage s+1 cannot touch a row before
 // stage s has finished the row below it, and by then stage s has long read everything it needs of
-// it.  A waiting warp sleeps in mbarrier.try_wait; there is no block barrier in the row loop, so a
-// slow step of one warp is absorbed by the slack of the ring instead of stalling all the others.
+// it.  The first look at a counter is issued before the step's own loads, so in the steady state the
+// wait costs no latency at all; there is no block barrier in the row loop, and a slow step of one warp is
+// absorbed by the slack of the ring instead of stalling all the others.  (An earlier version kept the
+// progress in rings of mbarriers: mbarrier.try_wait costs ~90 cycles even when the phase is complete,
+// two or three of them per step made the step longer than the per-row barrier they replaced.)
 //
-// The prologue and the epilogue of the pass are folded into the first and the last stage:
-//   * prolongation + correction: a Gauss-Seidel update never reads its own old value, so only the
-//     nodes of the SECOND colour need the correction before the first half-sweep, and stage 0 reads
-//     each of them exactly once (as its lower neighbours): it adds P(coarse u) on the fly and stores
-//     the corrected values back for the strip-half edges;
-//   * residual: after its update of row i the last stage holds the final values of every
-//     neighbour of the first-colour nodes of row i-1 in registers (its targets of the last three
-//     steps), so their residual costs three vector loads (rhs, v1, v2); the residual of its own
-//     targets costs none.  Injection needs the even columns of even rows only: every other step.
-// Shared-memory traffic per node and pass: about 160 B (down leg) / 180 B (up leg).
+// Every role of the pipeline is a pair of warps doing about the same work per row, so that no role paces the
+// others: the prolongation + correction has a role of its own in front of stage 0 (it touches the nodes of the
+// second colour only: a Gauss-Seidel update never reads its own old value, so the first colour is overwritten
+// unread), and the residual epilogue a role of its own behind the last stage, built like a half-sweep on the
+// first colour (the last stage sums the second colour's residual itself: all its operands are in registers).
+// (Folding both into stage 0 and the last stage saves shared-memory traffic but makes those two warps do 2-3
+// times the work of the others, and the pipeline runs at the pace of its slowest warp: measured slower.)
 //
-// Warps: 2 per stage (64 column pairs each, one 16-byte vector = 2 nodes per lane) + 1 producer.
+// Warps: 2 per role (64 column pairs each, one 16-byte vector = 2 nodes per lane) + 1 producer.
 #pragma once
 #include "common.cuh"
 #include "stream_pass.cuh"
@@ -56,21 +57,11 @@ constexpr int NGROUP = RING / GROUP;
 constexpr int CROWS = 3;       // coarse rows travelling with a group of fine rows
 constexpr int KMAX = 3;
 constexpr int NSTW = 2;        // warps per half-sweep stage (64 pairs each)
-constexpr int NSTAGE = 2 * KMAX * NSTW;
+constexpr int NPAIR = 2 * KMAX + 2;      // half-sweep stages + the prolongation role + the residual role
+constexpr int NSTAGE = NPAIR * NSTW;      // warps of those roles (a progress counter each)
 constexpr int WARPS = NSTAGE + 1;
 constexpr int THREADS = WARPS * 32;
 constexpr int PRODUCER_WARP = NSTAGE;
-// progress barriers per stage warp: step k is published on slot k % PBSLOTS.  How far a warp can run
-// ahead of one that waits for it is bounded by the ring (a stage cannot pass the load front, and the load
-// front cannot pass the last stage by more than RING rows) plus the steps after the last staged row
-// (at most 4 KMAX, none of which waits for data): with PBSLOTS beyond that a slot cannot complete
-// twice before its waiter has looked at it.
-constexpr int PBSLOTS = 64;
-static_assert(PBSLOTS > RING + 4 * KMAX && (PBSLOTS & (PBSLOTS - 1)) == 0, "progress barrier ring too short");
-// the last stage has read ring row r-1 for the last time once it has completed its step on row r
-// (that step still needs rhs / v1 / v2 of row r-1 for the residual)
-constexpr int REFILL_ROW = RING - GROUP;   // group g may be requested once the last stage is done with row (first row of g) - REFILL_ROW
-
 // opaque storage for a CUtensorMap (128 bytes, 64-byte aligned); filled by the host launcher
 struct alignas(64) TensorMapStorage { unsigned long long q[16]; };
 
@@ -114,7 +105,7 @@ struct Smem {
     unsigned char* raw;        // start of the dynamic shared memory (generic address; host emulation)
     unsigned base32;           // its shared-space address (device only)
     unsigned full_off;         // byte offset of the NGROUP load-completion barriers
-    unsigned pb_off;           // byte offset of the NSTAGE x PBSLOTS progress barriers
+    unsigned pb_off;           // byte offset of the progress counters: one unsigned per stage warp, the two warps of a stage adjacent
 };
 // byte offsets from `raw`: U ring at 0, rhs / v1 / v2 rings at ringb, 2 ringb, 3 ringb, the coarse
 // rows [NGROUP][CROWS][2][CW] at 4 ringb, then the barriers
@@ -123,7 +114,7 @@ enum Field { FIELD_U = 0, FIELD_F = 1, FIELD_V1 = 2, FIELD_V2 = 3, FIELD_C = 4 }
 
 constexpr size_t smem_bytes(int swk)
 {
-    return (size_t)4 * RING * 2 * swk * 8 + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8) * 8 + NGROUP * 8 + NSTAGE * PBSLOTS * 8 + 128;
+    return (size_t)4 * RING * 2 * swk * 8 + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8) * 8 + NGROUP * 8 + NSTAGE * 4 + 128;
 }
 constexpr size_t SMEM_BYTES = smem_bytes(SWK_MAX);
 
@@ -164,10 +155,13 @@ SY_FN void sy_full_expect(const Smem& sm, int g, unsigned bytes);
 SY_FN void sy_tma_load(const Params& p, const Smem& sm, int which, unsigned soff, int x, int z, int g);
 SY_FN void sy_tma_prefetch(const Params& p, int which, int x, int z);   // same box, into L2 only
 SY_FN void sy_full_wait(const Smem& sm, int g, unsigned parity);
-// progress barriers: one arrival (an elected lane, after sy_syncwarp) completes a phase; the wait
-// has acquire semantics for the whole warp's earlier shared-memory writes
-SY_FN void sy_pb_arrive(const Smem& sm, int warp, int slot);
-SY_FN void sy_pb_wait(const Smem& sm, int warp, int slot, unsigned parity);
+// progress counters: steps completed by a stage warp.  Publish = store-release by one lane after
+// sy_syncwarp (orders the whole warp's earlier shared-memory writes); peek = load-acquire of the
+// counters of both warps of a stage.
+struct Prog2 { unsigned h0, h1; };
+SY_FN void sy_prog_publish(const Smem& sm, int warp, unsigned steps_done);
+SY_FN Prog2 sy_prog_peek(const Smem& sm, int stage);
+SY_FN void sy_backoff();                                 // between two unsuccessful peeks
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes);
 SY_FN void sy_store_commit();
 SY_FN void sy_store_wait_read0();                        // every committed store has read its shared memory
@@ -209,47 +203,61 @@ SY_FN unsigned ring_adv(unsigned a, const Geo& g, unsigned lim)
     return a >= lim ? a - g.ringb : a;
 }
 
-SY_FN int first_step(const Tile& tl) { return tl.R0; }
-// the last stage works on row t - 4K + 1 in step t and must still visit row rb1 + 1 (residual of row rb1)
-SY_FN int last_step(const Params& p, const Tile& tl) { return tl.rb1 + 4 * p.K; }
 SY_FN int num_groups(const Tile& tl) { return (tl.R1 - tl.R0) / GROUP + 1; }
 
-// per-thread state of a stage warp, advanced by one row per step
+// Roles.  Every role is a pair of warps (column halves) walking down the rows one row per step; role R at
+// step k (t = R0 + k) works on row t - off(R):
+//   PRE      (passes with prolongation) row t: adds P(coarse u) to the SECOND-colour nodes (a Gauss-Seidel update
+//            never reads its own old value, so the first colour is overwritten unread)            off = 0
+//   stage s  half-sweep s (colour s & 1), s = 0 .. 2K-1                                           off = 1 + 2s (+1 with PRE)
+//   EPI      (passes with a residual epilogue) residual of the FIRST-colour nodes behind the last stage:
+//            injection of the even columns of even rows, or sum of squares (the second colour's
+//            residual is summed by the last stage itself: all its operands are in registers)      off = off(last) + 2
+// Pair index in the progress counters: stage s -> s, PRE -> 2 KMAX, EPI -> 2 KMAX + 1.
+constexpr int PAIR_PRE = 2 * KMAX, PAIR_EPI = 2 * KMAX + 1;
+
+SY_FN int off_stage(const Params& p, int s) { return 1 + 2 * s + (p.pre ? 1 : 0); }
+SY_FN int off_epi(const Params& p) { return off_stage(p, 2 * p.K - 1) + 2; }
+// the slowest role must still visit row rb1
+SY_FN int last_step(const Params& p, const Tile& tl) { return tl.rb1 + (p.post != POST_NONE ? off_epi(p) : off_stage(p, 2 * p.K - 1)); }
+
+// per-thread state of a role, advanced by one row per step
 struct Stage {
-    int s, h;           // stage, column half
+    int pair;           // own pair index in the progress counters
+    int up;             // pair index of the role whose results this one reads (-1: the TMA full barriers)
+    int h;              // column half
+    int s;              // stage number (colour = s & 1; the EPI role counts as stage 2K: first colour)
     int kk;             // first local pair of the lane's vector (even)
-    int row;            // the stage's row at the current step: t - 1 - 2s
-    int lo, hi;         // rows the stage updates: [lo, hi]
+    int off;            // row = t - off
+    int row;            // the role's row at the current step
+    int lo, hi;         // rows the role updates: [lo, hi]
     unsigned a_prev, a_cur, a_next;   // ring offsets of even-run element kk of rows row-1, row, row+1
     unsigned lim;       // ringb + kk*8: wrap limit of those offsets
     unsigned okp0, okp1;   // update masks of the lane's two targets for column parity 0 / 1 (scalars: a dynamically
                            // indexed array would live in local memory)
     bool outer_l, outer_r;            // the lane's left / right side neighbour lies outside the strip
-    bool live;          // the lane's vector lies inside the strip (strips narrower than the stage's 64 x NSTW pairs)
+    bool live;          // the lane's vector lies inside the strip (strips narrower than the role's 64 x NSTW pairs)
     // operands carried in registers from step to step: the other-parity nodes of the current row become
     // the next row's upper neighbours, the nodes loaded from the row below become the next row's
-    // horizontal neighbours (no other stage writes them in between: stage s+1 is two rows behind)
+    // horizontal neighbours (no other role writes them in between: the next one is two rows behind)
     D2 c_up, c_mid;
-    // last stage, residual epilogue: its (effective) targets of the previous two steps
-    D2 o1, o2;
     unsigned rmask0, rmask1;   // owned nodes with an interior column, per column parity
     int elo, ehi;       // owned interior rows
     double acc;         // POST_NORM2 accumulator
-    // stage 0 of a pass with prolongation
-    unsigned cmask0, cmask1;   // interior-column bits per column parity
+    unsigned cmask0, cmask1;   // interior-column bits per column parity (PRE)
 };
 
-SY_FN Stage init_stage(const Params& p, const Tile& tl, const Geo& geo, int warp, int lane)
+SY_FN Stage init_role(const Params& p, const Tile& tl, const Geo& geo, int pair, int up, int s, int off, int h, int lane)
 {
     Stage st;
-    st.s = warp / NSTW; st.h = warp % NSTW;
-    int kk = 64 * st.h + 2 * lane;
+    st.pair = pair; st.up = up; st.s = s; st.h = h; st.off = off;
+    int kk = 64 * h + 2 * lane;
     if (kk > p.SWK - 2) kk = p.SWK - 2;               // lanes beyond the strip shadow its last vector (all their masks are 0)
-    const bool live = 64 * st.h + 2 * lane < p.SWK;
+    const bool live = 64 * h + 2 * lane < p.SWK;
     st.kk = kk;
-    st.row = tl.R0 - 1 - 2 * st.s;
+    st.row = tl.R0 - off;
     st.lo = tl.R0 + 1; st.hi = tl.R1 - 1;             // rows row-1 and row+1 must be staged
-    st.c_up = D2{0.0, 0.0}; st.c_mid = D2{0.0, 0.0}; st.o1 = D2{0.0, 0.0}; st.o2 = D2{0.0, 0.0};
+    st.c_up = D2{0.0, 0.0}; st.c_mid = D2{0.0, 0.0};
     st.acc = 0.0;
     st.elo = tl.rb0 < 1 ? 1 : tl.rb0; st.ehi = tl.rb1 > p.n - 1 ? (int)p.n - 1 : tl.rb1;
     st.okp0 = st.okp1 = st.rmask0 = st.rmask1 = st.cmask0 = st.cmask1 = 0;
@@ -271,7 +279,6 @@ SY_FN Stage init_stage(const Params& p, const Tile& tl, const Geo& geo, int warp
     st.live = live;
     st.outer_l = kk == 0;
     st.outer_r = kk + 2 >= p.SWK;
-    const int off = 1 + 2 * st.s;                                    // row = t - off
     const int slot = ((RING - off) % RING + RING) % RING;            // row R0 sits in slot 0
     st.lim = geo.ringb + (unsigned)kk * 8u;
     st.a_cur = (unsigned)slot * geo.rowb + (unsigned)kk * 8u;
@@ -286,132 +293,152 @@ SY_FN void advance_row(const Geo& geo, Stage& st)
     st.a_prev = st.a_cur; st.a_cur = st.a_next; st.a_next = ring_adv(st.a_next, geo, st.lim);
 }
 
-SY_FN void pb_wait_step(const Smem& sm, int warp, int k)
+// wait until the warps of pair `pair` have completed `need0` / `need1` steps (pv: a peek taken earlier)
+SY_FN void prog_wait(const Smem& sm, int pair, unsigned need0, unsigned need1, Prog2 pv)
 {
-    sy_pb_wait(sm, warp, k & (PBSLOTS - 1), (unsigned)(k / PBSLOTS) & 1u);
+    while (pv.h0 < need0 || pv.h1 < need1) { sy_backoff(); pv = sy_prog_peek(sm, pair); }
 }
 
-// bilinear prolongation (gs.cpp:238-240) of the coarse iterate at the lane's two nodes of column
-// parity PAR in fine row `t` (whose second-colour nodes have exactly that parity: even columns of odd
-// rows, odd columns of even rows).  g: the TMA group of row t, G0: its first row.
-// Coarse column (k0 + k) sits at local index k: even k in the E run at k/2, odd k in the O run at k/2.
-SY_FN D2 prolong_pair(const Params& p, const Geo& geo, const Smem& sm, const Stage& st, int PAR, int t, int gslot, int G0)
+// wait for the data of step k: the TMA group of row t (roles fed by the TMA engine) or step k-1 of the role above
+SY_FN void wait_inputs(const Tile& tl, const Geo& geo, const Smem& sm, const Stage& st, int k, Prog2 seen)
 {
-    const int crow = (t >> 1) - (G0 >> 1);                           // 0..2; an odd fine row also uses crow+1
-    const unsigned c0 = 4u * geo.ringb + (unsigned)gslot * geo.cgrpb + (unsigned)crow * 2u * geo.cwb + (unsigned)(st.kk >> 1) * 8u;
-    const double a0 = sy_lds1(sm, c0), a1 = sy_lds1(sm, c0 + geo.cwb);
-    D2 e;
-    if (PAR) {                                                       // even row, odd columns (gs.cpp:240)
-        const double a2 = sy_lds1(sm, c0 + 8u);
-        e.x = __dmul_rn(__dadd_rn(a0, a1), 0.5); e.y = __dmul_rn(__dadd_rn(a1, a2), 0.5);
-    } else {                                                         // odd row, even columns (gs.cpp:239)
-        const unsigned c1 = c0 + 2u * geo.cwb;
-        const double b0 = sy_lds1(sm, c1), b1 = sy_lds1(sm, c1 + geo.cwb);
-        e.x = __dmul_rn(__dadd_rn(a0, b0), 0.5); e.y = __dmul_rn(__dadd_rn(a1, b1), 0.5);
+    if (st.up < 0) {
+        const int t = tl.R0 + k;
+        if ((k & (GROUP - 1)) == 0 && t <= tl.R1) {
+            const int g = k / GROUP;
+            sy_full_wait(sm, g % NGROUP, (unsigned)(g / NGROUP) & 1u);
+        }
+    } else {
+        prog_wait(sm, st.up, (unsigned)k, geo.nh == 2 ? (unsigned)k : 0u, seen);
     }
-    return e;
+}
+
+SY_FN void publish(const Smem& sm, const Stage& st, int k)
+{
+    sy_syncwarp();
+    if (sy_elect()) sy_prog_publish(sm, st.pair * NSTW + st.h, (unsigned)k + 1u);
 }
 
 // ------------------------------------------------------------------------------------------
-// One step of a stage warp: the half-sweep on row st.row (colour = stage & 1), one 16-byte vector
-// per lane, PAR = the column parity of that colour in this row.  With pair index kk even, the
-// horizontal neighbours of targets (kk, kk+1) are three consecutive nodes of the OTHER run: from
-// kk-1 (even columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd columns: E[kk], E[kk+1], E[kk+2]).
-//   FIRST   stage 0: waits for the TMA group of the row below instead of an upstream stage
-//   PRE     (with FIRST) adds the prolongated coarse iterate to the nodes it loads from the row below
-//   LAST    the warp's rows go to the bulk-store engine; EPI: residual epilogue kind
-//   CHECKED the step may touch rows above R0 (first steps of a tile): loads of unstaged rows are skipped
-template <int ARITH, bool FIRST, bool PRE, bool LAST, int EPI>
+// PRE role, step k: row t = R0 + k.  Bilinear prolongation (gs.cpp:238-240) of the coarse iterate at the lane's
+// two SECOND-colour nodes of the row (even columns of odd rows, odd columns of even rows) added to u
+// (multigrid.cpp:83), interior nodes only.  The coarse rows of a group start at coarse row (first fine row of
+// the group) >> 1; coarse column (k0 + k) sits at local index k: even k in the E run at k/2, odd k in the O run.
+SY_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, Stage& st, const int k)
+{
+    const int t = st.row;
+    wait_inputs(tl, geo, sm, st, k, Prog2{0u, 0u});
+    if (t >= tl.R0 && t <= tl.R1 && t >= 1 && t <= (int)p.n - 1) {
+        const int PAR = (t + 1) & 1;
+        const unsigned a = st.a_cur + (PAR ? geo.swkb : 0u);
+        const int g = k / GROUP, G0 = tl.R0 + g * GROUP;
+        const int crow = (t >> 1) - (G0 >> 1);                       // 0..2; an odd fine row also uses crow+1
+        const unsigned c0 = 4u * geo.ringb + (unsigned)(g % NGROUP) * geo.cgrpb + (unsigned)crow * 2u * geo.cwb + (unsigned)(st.kk >> 1) * 8u;
+        D2 u{0.0, 0.0};
+        if (st.live) u = sy_lds2(sm, a);
+        const double a0 = sy_lds1(sm, c0), a1 = sy_lds1(sm, c0 + geo.cwb);
+        D2 e;
+        if (PAR) {                                                   // even row, odd columns (gs.cpp:240)
+            const double a2 = sy_lds1(sm, c0 + 8u);
+            e.x = __dmul_rn(__dadd_rn(a0, a1), 0.5); e.y = __dmul_rn(__dadd_rn(a1, a2), 0.5);
+        } else {                                                     // odd row, even columns (gs.cpp:239)
+            const unsigned c1 = c0 + 2u * geo.cwb;
+            const double b0 = sy_lds1(sm, c1), b1 = sy_lds1(sm, c1 + geo.cwb);
+            e.x = __dmul_rn(__dadd_rn(a0, b0), 0.5); e.y = __dmul_rn(__dadd_rn(a1, b1), 0.5);
+        }
+        const unsigned cm = PAR ? st.cmask1 : st.cmask0;
+        u.x = __dadd_rn(u.x, e.x); u.y = __dadd_rn(u.y, e.y);
+        if (cm == 3u) sy_sts2(sm, a, u);
+        else {
+            if (cm & 1u) sy_sts1(sm, a, u.x);
+            if (cm & 2u) sy_sts1(sm, a + 8u, u.y);
+        }
+    }
+    publish(sm, st, k);
+    advance_row(geo, st);
+}
+
+SY_FN void pre_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, Stage& st)
+{
+    const int klast = last_step(p, tl) - tl.R0;
+    for (int k = 0; k <= klast; ++k) pre_step(p, tl, geo, sm, st, k);
+}
+
+// ------------------------------------------------------------------------------------------
+// One step of a half-sweep stage (RESID = false) or of the EPI role (RESID = true) on row st.row, one 16-byte
+// vector per lane, PAR = the column parity of the role's colour in this row.  With pair index kk even, the
+// horizontal neighbours of targets (kk, kk+1) are three consecutive nodes of the OTHER run: from kk-1 (even
+// columns: O[kk-1], O[kk], O[kk+1]) or from kk (odd columns: E[kk], E[kk+1], E[kk+2]).
+//   LAST    the warp's rows go to the bulk-store engine; NORM1: it also sums the residual of its own targets
+//   RESID   nothing is updated: the residual of the nodes is injected (EPI = POST_INJECT: even columns of even
+//           rows) or squared and summed (POST_NORM2)
+//   CHECKED the step may touch rows outside [R0, R1] (first and last steps of a tile): their loads are skipped
+template <int ARITH, bool LAST, bool NORM1, bool RESID, int EPI>
 SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, Stage& st, const int k, const int PAR,
                       const bool CHECKED)
 {
     const unsigned po = PAR ? geo.swkb : 0u, oo = PAR ? 0u : geo.swkb;
     const unsigned c = st.a_cur + po;
     const int row = st.row;
-    // is the row itself / the row below staged?  (first and last steps of a tile only; a lane outside the strip
-    // shadows the last live vector and must not load what that lane is storing)
+    // is the row itself / the row below staged?  (a lane outside the strip shadows the last live vector and
+    // must not load what that lane is storing)
     const bool own_ok = !CHECKED || (row >= tl.R0 && row <= tl.R1);
     const bool dn_ok = !CHECKED || (row + 1 >= tl.R0 && row + 1 <= tl.R1);
-    const int w = st.s * NSTW + st.h;
-    // ---- before the wait: everything that does not depend on the upstream stage's last step
-    D2 f{0.0, 0.0}, w1{0.0, 0.0}, w2{0.0, 0.0};
+    // ---- first look at the counters this step depends on: issued before the step's own loads, so that in the
+    // steady state the answer is there when it is needed
+    Prog2 seen{0u, 0u};
+    if (st.up >= 0) seen = sy_prog_peek(sm, st.up);
+    // ---- before the wait: everything that does not depend on the last step of the role above
+    const bool work = !RESID || EPI == POST_NORM2 || PAR == 0;       // injection: even columns (of even rows) only
+    D2 f{0.0, 0.0}, w1{0.0, 0.0}, w2{0.0, 0.0}, own{0.0, 0.0};
     double x = 0.0;
     const D2 up = st.c_up, m = st.c_mid;
-    if (FIRST && PRE && geo.nh == 2 && k >= 1) pb_wait_step(sm, w ^ 1, k - 1);   // the other half's corrected edge node
-    if (own_ok) {
-        if (st.live) { f = sy_lds2(sm, c + geo.ringb); w1 = sy_lds2(sm, c + 2u * geo.ringb); w2 = sy_lds2(sm, c + 3u * geo.ringb); }
-        x = sy_side(sm, m, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u), PAR ? 1 : -1, PAR ? st.outer_r : st.outer_l);
+    if (work && own_ok && st.live) {
+        f = sy_lds2(sm, c + geo.ringb); w1 = sy_lds2(sm, c + 2u * geo.ringb); w2 = sy_lds2(sm, c + 3u * geo.ringb);
+        if (RESID) own = sy_lds2(sm, c);
     }
+    if (work && own_ok) x = sy_side(sm, m, st.a_cur + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u), PAR ? 1 : -1, PAR ? st.outer_r : st.outer_l);
     const double n0 = PAR ? m.x : x, n1 = PAR ? m.y : m.x, n2 = PAR ? x : m.y;
     const Coef4 c0 = Arith<ARITH>::coef(w1.x, w2.x, p.st);
     const Coef4 c1 = Arith<ARITH>::coef(w1.y, w2.y, p.st);
-    const double h0 = Arith<ARITH>::gs_head(f.x, up.x, n0, c0);
-    const double h1 = Arith<ARITH>::gs_head(f.y, up.y, n1, c1);
-    // ---- wait for the data of the row below (and, last stage: for the other half's previous targets)
-    const int t = tl.R0 + k;                             // = row + 1 + 2s: the row below stage 0's
-    if (FIRST) {
-        if ((k & (GROUP - 1)) == 0 && t <= tl.R1) {
-            const int g = k / GROUP;
-            sy_full_wait(sm, g % NGROUP, (unsigned)(g / NGROUP) & 1u);
-        }
-    } else if (k >= 1) {
-        pb_wait_step(sm, w - NSTW, k - 1);
-        if (geo.nh == 2) pb_wait_step(sm, (w - NSTW) ^ 1, k - 1);
-    }
-    if (EPI != POST_NONE && geo.nh == 2 && k >= 1) pb_wait_step(sm, w ^ 1, k - 1);
+    double h0 = 0.0, h1 = 0.0;
+    if (!RESID) { h0 = Arith<ARITH>::gs_head(f.x, up.x, n0, c0); h1 = Arith<ARITH>::gs_head(f.y, up.y, n1, c1); }
+    // ---- wait for the data of the row below
+    wait_inputs(tl, geo, sm, st, k, seen);
     // ---- after the wait
     D2 dn{0.0, 0.0};
     if (dn_ok && st.live) dn = sy_lds2(sm, st.a_next + po);
-    if (FIRST && PRE && dn_ok && t >= 1 && t <= (int)p.n - 1) {
-        // multigrid.cpp:83 on the second-colour nodes of row t (the first colour is overwritten unread)
-        const int g = k / GROUP;
-        const D2 e = prolong_pair(p, geo, sm, st, PAR, t, g % NGROUP, tl.R0 + g * GROUP);
-        const unsigned cm = PAR ? st.cmask1 : st.cmask0;
-        if (cm & 1u) dn.x = __dadd_rn(dn.x, e.x);
-        if (cm & 2u) dn.y = __dadd_rn(dn.y, e.y);
-        if (cm == 3u) sy_sts2(sm, st.a_next + po, dn);
-        else {
-            if (cm & 1u) sy_sts1(sm, st.a_next + po, dn.x);
-            if (cm & 2u) sy_sts1(sm, st.a_next + po + 8u, dn.y);
-        }
-    }
-    const double o0 = Arith<ARITH>::gs_tail(h0, dn.x, n1, c0.d, c0.b, p.st);
-    const double o1 = Arith<ARITH>::gs_tail(h1, dn.y, n2, c1.d, c1.b, p.st);
-    const bool act = row >= st.lo && row <= st.hi;
-    const unsigned okb = act ? (PAR ? st.okp1 : st.okp0) : 0u;
     const unsigned rm = PAR ? st.rmask1 : st.rmask0;
-    // one 16-byte store in the common case: two 8-byte stores at a 16-byte lane stride cost twice the wavefronts
-    if (okb == 3u) sy_sts2(sm, c, D2{o0, o1});
-    else {
-        if (okb & 1u) sy_sts1(sm, c, o0);
-        if (okb & 2u) sy_sts1(sm, c + 8u, o1);
-    }
-    if (EPI != POST_NONE) {
-        // what the ring now holds at the lane's targets: the new value, or the old one where masked
-        D2 oe{o0, o1};
-        if (okb != 3u) {
-            D2 old{0.0, 0.0};
-            if (own_ok && st.live) old = sy_lds2(sm, c);
-            if (!(okb & 1u)) oe.x = old.x;
-            if (!(okb & 2u)) oe.y = old.y;
+    if (!RESID) {
+        const double o0 = Arith<ARITH>::gs_tail(h0, dn.x, n1, c0.d, c0.b, p.st);
+        const double o1 = Arith<ARITH>::gs_tail(h1, dn.y, n2, c1.d, c1.b, p.st);
+        const bool act = row >= st.lo && row <= st.hi;
+        const unsigned okb = act ? (PAR ? st.okp1 : st.okp0) : 0u;
+        // one 16-byte store in the common case: two 8-byte stores at a 16-byte lane stride cost twice the wavefronts
+        if (okb == 3u) sy_sts2(sm, c, D2{o0, o1});
+        else {
+            if (okb & 1u) sy_sts1(sm, c, o0);
+            if (okb & 2u) sy_sts1(sm, c + 8u, o1);
         }
-        // residual (gs.cpp:75) of the FIRST-colour nodes of row q = row-1 (run PAR): own value = up,
-        // upper neighbour = the targets of two steps ago, lower = this step's, horizontal = last step's
-        const int q = row - 1;
-        if ((EPI == POST_NORM2 || PAR == 0) && q >= st.elo && q <= st.ehi) {
-            const unsigned cq = st.a_prev + po;
-            D2 fq{0.0, 0.0}, a{0.0, 0.0}, b{0.0, 0.0};
-            if (st.live) { fq = sy_lds2(sm, cq + geo.ringb); a = sy_lds2(sm, cq + 2u * geo.ringb); b = sy_lds2(sm, cq + 3u * geo.ringb); }
-            const double xq = sy_side(sm, st.o1, st.a_prev + oo + (PAR ? 16u : 0u) - (PAR ? 0u : 8u), PAR ? 1 : -1,
-                                      PAR ? st.outer_r : st.outer_l);
-            const double m0 = PAR ? st.o1.x : xq, m1 = PAR ? st.o1.y : st.o1.x, m2 = PAR ? xq : st.o1.y;
-            const Coef4 q0 = Arith<ARITH>::coef(a.x, b.x, p.st), q1 = Arith<ARITH>::coef(a.y, b.y, p.st);
-            const double r0 = Arith<ARITH>::residual(fq.x, up.x, st.o2.x, m0, oe.x, m1, q0, p.st);
-            const double r1 = Arith<ARITH>::residual(fq.y, up.y, st.o2.y, m1, oe.y, m2, q1, p.st);
+        // the row is written: publish (the last stage's rows go to the bulk-store engine: generic -> async proxy first)
+        if (LAST) sy_fence_async();
+        publish(sm, st, k);
+        if (NORM1 && row >= st.elo && row <= st.ehi) {
+            // gs.cpp:75 on the nodes just updated, every operand in registers (owned nodes are never masked)
+            const double r0 = Arith<ARITH>::residual(f.x, o0, up.x, n0, dn.x, n1, c0, p.st);
+            const double r1 = Arith<ARITH>::residual(f.y, o1, up.y, n1, dn.y, n2, c1, p.st);
+            if (rm & 1u) st.acc += r0 * r0;
+            if (rm & 2u) st.acc += r1 * r1;
+        }
+    } else {
+        publish(sm, st, k);                              // nothing written: only the rows' release is signalled
+        if (work && row >= st.elo && row <= st.ehi && (EPI == POST_NORM2 || (row & 1) == 0)) {
+            const double r0 = Arith<ARITH>::residual(f.x, own.x, up.x, n0, dn.x, n1, c0, p.st);
+            const double r1 = Arith<ARITH>::residual(f.y, own.y, up.y, n1, dn.y, n2, c1, p.st);
             if (EPI == POST_INJECT) {
-                // gs.cpp:283: coarse node (q/2, kg) for fine even column 2kg; kg even -> E run, kg+1 -> O run
+                // gs.cpp:283: coarse node (row/2, kg) for fine even column 2kg; kg even -> E run, kg+1 -> O run
                 const long kg = (long)tl.k0 + st.kk;
-                double* crow = p.crhs + ((long)(q >> 1) - p.crow0) * p.cpitch + (kg >> 1);
+                double* crow = p.crhs + ((long)(row >> 1) - p.crow0) * p.cpitch + (kg >> 1);
                 if (st.rmask0 & 1u) crow[0] = r0;
                 if (st.rmask0 & 2u) crow[p.codd] = r1;
             } else {
@@ -419,43 +446,31 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
                 if (rm & 2u) st.acc += r1 * r1;
             }
         }
-        if (EPI == POST_NORM2 && row >= st.elo && row <= st.ehi) {
-            // the second colour: the nodes just updated, every operand in registers
-            const double r0 = Arith<ARITH>::residual(f.x, o0, up.x, n0, dn.x, n1, c0, p.st);
-            const double r1 = Arith<ARITH>::residual(f.y, o1, up.y, n1, dn.y, n2, c1, p.st);
-            if (rm & 1u) st.acc += r0 * r0;
-            if (rm & 2u) st.acc += r1 * r1;
-        }
-        st.o2 = st.o1; st.o1 = oe;
     }
-    if (LAST) sy_fence_async();
     st.c_up = m; st.c_mid = dn;
-    // ---- publish the step
-    sy_syncwarp();
-    if (sy_elect()) sy_pb_arrive(sm, w, k & (PBSLOTS - 1));
     advance_row(geo, st);
 }
 
-template <int ARITH, bool FIRST, bool PRE, bool LAST, int EPI>
+template <int ARITH, bool LAST, bool NORM1, bool RESID, int EPI>
 SY_FN void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, Stage& st)
 {
-    const int klast = last_step(p, tl) - first_step(tl);
-    // column parity of the stage's colour in its row at step k: (s + row) & 1 with row = R0 + k - 1 - 2s
+    const int klast = last_step(p, tl) - tl.R0;
+    // column parity of the role's colour in its row: (s + row) & 1
     int par = (st.s + st.row) & 1;
     int k = 0;
     // first steps: rows above R0 (checked); then align the unrolled loop on parity 0; last steps: rows below R1
-    // (checked: the slots of unstaged rows may still be in use by the stages behind)
-    const int kchk = 2 * st.s + 1;                       // first step with row >= R0
-    int kmain = tl.R1 - tl.R0 + 2 * st.s;                // last step with row + 1 <= R1
+    // (checked: the slots of unstaged rows may still be in use by the roles behind)
+    const int kchk = st.off;                             // first step with row >= R0
+    int kmain = tl.R1 - tl.R0 + st.off - 1;              // last step with row + 1 <= R1
     if (kmain > klast) kmain = klast;
     for (; k <= klast && (k < kchk || par != 0); ++k, par ^= 1)
-        stage_step<ARITH, FIRST, PRE, LAST, EPI>(p, tl, geo, sm, st, k, par, true);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, par, true);
     for (; k + 1 <= kmain; k += 2) {
-        stage_step<ARITH, FIRST, PRE, LAST, EPI>(p, tl, geo, sm, st, k, 0, false);
-        stage_step<ARITH, FIRST, PRE, LAST, EPI>(p, tl, geo, sm, st, k + 1, 1, false);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, 0, false);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k + 1, 1, false);
     }
     for (; k <= klast; ++k, par ^= 1)
-        stage_step<ARITH, FIRST, PRE, LAST, EPI>(p, tl, geo, sm, st, k, par, true);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, par, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -487,39 +502,45 @@ SY_FN void issue_group_loads(const Params& p, const Tile& tl, const Geo& geo, co
     }
 }
 
-// The producer follows the last stage: in step k that stage finishes row r = t - 4K + 1.  The row is
-// stored as soon as both of its warps have published the step; group g is requested once the last
-// stage has completed row (first row of g) - REFILL_ROW, its last use of the slot's previous rows
-// (rhs / v1 / v2 of the row above for the residual).
+// The producer follows the last stage and the last role.  In step k the last stage finishes row rs = t - off(last):
+// the row is stored as soon as both of its warps have published the step.  Ring rows are released by the LAST
+// ROLE (the EPI role if the pass has one, else the last stage): once it has published its step on row rl it needs
+// no row <= rl any more (what it still uses of row rl+1 it carries in registers), so group g (first row G), which
+// replaces rows G-RING .. G-RING+GROUP-1, is requested once row G-RING+GROUP-1 is published -- after the bulk stores
+// issued so far have read their rows.
 SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
 {
     const int ng = num_groups(tl);
     int gnext = 0;
     for (; gnext < ng && gnext < NGROUP; ++gnext) issue_group_loads(p, tl, geo, sm, gnext);   // fresh slots
-    const int klast = last_step(p, tl) - first_step(tl);
-    const int wl = (2 * p.K - 1) * NSTW;                 // the last stage's first warp
+    const int klast = last_step(p, tl) - tl.R0;
+    const int pair_s = 2 * p.K - 1, off_s = off_stage(p, pair_s);
+    const bool epi = p.post != POST_NONE;
+    const int pair_l = epi ? PAIR_EPI : pair_s, off_l = epi ? off_epi(p) : off_s;
     long eE = (long)tl.kb + p.WK, eO = eE;
     if (eE > p.nhalf + 1) eE = p.nhalf + 1;
     if (eO > p.nhalf) eO = p.nhalf;
     const unsigned nE8 = (unsigned)(((eE - tl.kb + 1) & ~1L) * 8);   // whole 16-byte units (the layout has slack)
     const unsigned nO8 = (unsigned)((eO - tl.kb) * 8);
-    int r = tl.R0 - 4 * p.K + 1;                                     // the last stage's row in step 0
-    double* gst = p.u_out + ((long)r - p.row0) * p.pitch + tl.kb;
-    unsigned a = (unsigned)((((r - tl.R0) % RING) + RING) % RING) * geo.rowb + (unsigned)HK * 8u;
-    for (int k = 0; k <= klast; ++k, ++r) {
-        const bool store = r >= tl.rb0 && r <= tl.rb1;
-        const bool load = gnext < ng && r >= tl.R0 + GROUP * gnext - REFILL_ROW;
-        if (store || load) {
-            pb_wait_step(sm, wl, k);
-            if (geo.nh == 2) pb_wait_step(sm, wl + 1, k);
-        }
-        if (store && sy_elect()) {
-            if (nE8) sy_bulk_store(sm, gst, a, nE8);
-            if (nO8) sy_bulk_store(sm, gst + p.odd, a + geo.swkb, nO8);
-            sy_store_commit();
+    int rs = tl.R0 - off_s, rl = tl.R0 - off_l;                      // the rows of the two roles in step 0
+    double* gst = p.u_out + ((long)rs - p.row0) * p.pitch + tl.kb;
+    unsigned a = (unsigned)((((rs - tl.R0) % RING) + RING) % RING) * geo.rowb + (unsigned)HK * 8u;
+    const unsigned need_h1 = geo.nh == 2 ? 1u : 0u;
+    for (int k = 0; k <= klast; ++k, ++rs, ++rl) {
+        const bool store = rs >= tl.rb0 && rs <= tl.rb1;
+        const bool load = gnext < ng && rl >= tl.R0 + GROUP * gnext - RING + GROUP - 1;
+        if (store) {
+            prog_wait(sm, pair_s, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_s));
+            if (sy_elect()) {
+                if (nE8) sy_bulk_store(sm, gst, a, nE8);
+                if (nO8) sy_bulk_store(sm, gst + p.odd, a + geo.swkb, nO8);
+                sy_store_commit();
+            }
         }
         if (load) {
-            if (sy_elect()) { if (store) sy_store_wait_read1(); else sy_store_wait_read0(); }
+            prog_wait(sm, pair_l, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_l));
+            // stores of rows <= rl must have left shared memory; the newest one (row rs > rl with an epilogue) may be in flight
+            if (sy_elect()) { if (store && epi) sy_store_wait_read1(); else sy_store_wait_read0(); }
             issue_group_loads(p, tl, geo, sm, gnext);
             ++gnext;
         }
@@ -543,11 +564,24 @@ SY_FN double run_warp(const Params& p, const Tile& tl, const Geo& geo, const Sme
         producer_loop(p, tl, geo, sm);
         return 0.0;
     }
-    const int s = warp / NSTW, h = warp % NSTW;
-    if (s >= 2 * p.K || h >= geo.nh) return 0.0;
-    Stage st = init_stage(p, tl, geo, warp, lane);
-    if (s == 0) stage_loop<ARITH, true, PRE, false, POST_NONE>(p, tl, geo, sm, st);
-    else if (s == 2 * p.K - 1) stage_loop<ARITH, false, false, true, POSTK>(p, tl, geo, sm, st);
+    const int pair = warp / NSTW, h = warp % NSTW;
+    if (h >= geo.nh) return 0.0;
+    const int last = 2 * p.K - 1;
+    if (pair == PAIR_PRE) {
+        if (!PRE) return 0.0;
+        Stage st = init_role(p, tl, geo, PAIR_PRE, -1, 1, 0, h, lane);
+        pre_loop(p, tl, geo, sm, st);
+        return 0.0;
+    }
+    if (pair == PAIR_EPI) {
+        if (POSTK == POST_NONE) return 0.0;
+        Stage st = init_role(p, tl, geo, PAIR_EPI, last, 2 * p.K, off_epi(p), h, lane);
+        stage_loop<ARITH, false, false, true, POSTK>(p, tl, geo, sm, st);
+        return st.acc;
+    }
+    if (pair > last) return 0.0;
+    Stage st = init_role(p, tl, geo, pair, pair == 0 ? (PRE ? PAIR_PRE : -1) : pair - 1, pair, off_stage(p, pair), h, lane);
+    if (pair == last) stage_loop<ARITH, true, POSTK == POST_NORM2, false, POST_NONE>(p, tl, geo, sm, st);
     else stage_loop<ARITH, false, false, false, POST_NONE>(p, tl, geo, sm, st);
     return st.acc;
 }

@@ -46,6 +46,35 @@ static __global__ void vecadd(double* a, double* b, double* c, long n)
     for (long i = mgb200_gscu_detail::linear_tid(); i < n; i += mgb200_gscu_detail::total_threads()) a[i] = __dadd_rn(b[i], c[i]);
 }
 
+// a[i] *= a[i] (gs.cu:13-17)
+static __global__ void square_ker(double* a, long n)
+{
+    for (long i = mgb200_gscu_detail::linear_tid(); i < n; i += mgb200_gscu_detail::total_threads()) a[i] = __dmul_rn(a[i], a[i]);
+}
+
+// sum[b] = a[b*B] + ... + a[b*B + B - 1] for block b of B = blockDim.x*blockDim.y threads (gs.cu:25-43): the block
+// layout IS the contract here, so this shim keeps it (pairwise tree like the reference, warp shuffles instead of
+// shared-memory halving).  The reference calls it in place (sum == a, gs.cu:54), where block b's store to a[b] races
+// with block 0's read of the same element; that hazard belongs to the call pattern, not to the kernel, and
+// compute_norm() below does not use it.
+static __global__ void reduction_kernel(double* sum, const double* a, long N)
+{
+    __shared__ double warp_sums[32];
+    const long nthr = (long)blockDim.x * blockDim.y;
+    const long tid = (long)threadIdx.y * blockDim.x + threadIdx.x;
+    const long block = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    const long idx = block * nthr + tid;
+    double v = idx < N ? a[idx] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_sums[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+        v = tid < (nthr + 31) / 32 ? warp_sums[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (tid == 0) sum[block] = v;
+    }
+}
+
 static __global__ void gpucopy(double* dest, const double* source, long n)
 {
     for (long i = mgb200_gscu_detail::linear_tid(); i < n; i += mgb200_gscu_detail::total_threads()) dest[i] = source[i];

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MGB200_VERSION 100
+#define MGB200_VERSION 200
 
 enum {
     MGB200_OK = 0,
@@ -239,6 +239,41 @@ int mgb200_timestepper_device(double *uT, const double *u0, const double *v1, co
                               double nu, int maxlvl, int n, double dt, double T, double dx,
                               double tol, int shape, const mgb200_options *opt,
                               mgb200_solve_info *last);
+/* ------------------------------------------------------------------------------------------
+ * mg_inner / mg_outer with the reference's own argument lists on CALLER-OWNED towers
+ * (multigrid.cpp:17-21, 97-99 = multigrid.cu:17-21, 101-103): u, rhs, v1, v2 are HOST arrays of maxlvl
+ * DEVICE pointers; level l is a dense (n_l+1)^2 array with row stride n_l+1 (n_l = n_0 / 2^l, whatever the
+ * size of its allocation: the reference gives every coarse level (N/2+1)^2 doubles); tmp is one device array
+ * of (n+1)^2 doubles re-used on every level with that level's stride (multigrid.cpp:162).  The cycle runs
+ * operator by operator in the reference's order on those arrays; opt (may be NULL) supplies niter,
+ * coarse_maxit, coarse_tol, max_cycle and arith -- the literals of multigrid.cpp:41,60,94 by default.
+ * mg_outer returns the history in *info (may be NULL) and warns on stderr like multigrid.cpp:117-119 when
+ * the tolerance was not met (MGB200_QUIET=1 silences it).  Both synchronise `stream` (the coarsest-level loop
+ * and the cycle loop test a norm on the host, as the reference does).
+ * ------------------------------------------------------------------------------------------ */
+int mgb200_mg_inner(double **u, double **rhs, double **v1, double **v2, double *tmp, double dx, int n,
+                    int lvl, int maxlvl, int shape, double dt, double nu, const mgb200_options *opt,
+                    void *stream);
+int mgb200_mg_outer(double **utow, double **v1tow, double **v2tow, double **rhstow, double *tmp,
+                    double nu, int maxlvl, int n, double dt, double dx, double tol, int shape,
+                    const mgb200_options *opt, void *stream, mgb200_solve_info *info);
+
+/* ------------------------------------------------------------------------------------------
+ * The gs.h operators on HOST pointers with gs.h's argument lists (gs.h:3-17; ld = n+1): each call
+ * copies its operands to the device, runs the operator above and copies the result back.  For
+ * operator-level drop-in and tests (include/compat/gs.h builds the reference's unmodified
+ * multigrid.cpp on them); a time loop should use the handle API, which keeps the fields in HBM.
+ * ------------------------------------------------------------------------------------------ */
+int mgb200_host_residual(double *res, const double *u, const double *rhs, long n, const double *v1,
+                         const double *v2, double k, double nu, double h, int arith);
+int mgb200_host_compute_norm(const double *res, long n, double *out);
+int mgb200_host_gauss_seidel(double *u, const double *rhs, long n, const double *v1, const double *v2,
+                             double k, double nu, double h, int iters, int arith);
+int mgb200_host_compute_rhs(double *rhs, const double *u, long n, const double *v1, const double *v2,
+                            double k, double nu, double h, int arith);
+int mgb200_host_prolongation(double *up, const double *u, int n);   /* n = COARSE n (gs.h:16) */
+int mgb200_host_restriction(double *u, const double *up, int n);    /* n = FINE n   (gs.h:17) */
+
 /* The one-call drivers keep their last handle (the level towers in HBM) alive and reuse it when
  * the next call has the same shape and parameters; this frees it. */
 int mgb200_release_cached(void);

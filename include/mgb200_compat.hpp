@@ -93,9 +93,29 @@ inline void timestepper_host(double* uT, double* u0, double* v1, double* v2, dou
     check(mgb200_timestepper_host(uT, u0, v1, v2, nu, maxlvl, n, dt, T, dx, tol, shape, &o, nullptr), "timestepper");
 }
 
-// mg_outer / mg_inner work on caller-owned towers in the reference (multigrid.cu:17-21,101-103).
-// The library owns its towers (split layout, no (N/2+1)^2 over-allocation), so the equivalents
-// are methods of a handle created from the level-0 fields:
+// mg_inner / mg_outer with the reference argument lists on CALLER-OWNED towers (multigrid.cu:17-21,
+// 101-103: host arrays of device pointers, level l dense with stride n_l+1, one spare array tmp).
+// The cycle runs operator by operator on those arrays, in the reference's order.
+inline void mg_inner(double** u, double** rhs, double** v1, double** v2, double* tmp, double dx, int n, int lvl, int maxlvl,
+                     int shape, double dt, double nu)
+{
+    mgb200_options o;
+    mgb200_default_options(&o);
+    o.arith = arithmetic();
+    check(mgb200_mg_inner(u, rhs, v1, v2, tmp, dx, n, lvl, maxlvl, shape, dt, nu, &o, nullptr), "mg_inner");
+}
+
+inline void mg_outer(double** utow, double** v1tow, double** v2tow, double** rhstow, double* tmp, double nu, int maxlvl, int n,
+                     double dt, double dx, double tol, int shape)
+{
+    mgb200_options o;
+    mgb200_default_options(&o);
+    o.arith = arithmetic();
+    check(mgb200_mg_outer(utow, v1tow, v2tow, rhstow, tmp, nu, maxlvl, n, dt, dx, tol, shape, &o, nullptr, nullptr), "mg_outer");
+}
+
+// The FUSED solver owns its towers (split layout, no (N/2+1)^2 over-allocation, one CUDA graph per
+// cycle), so its mg_inner / mg_outer are methods of a handle created from the level-0 fields:
 class Multigrid {
 public:
     Multigrid(int n, int maxlvl, double nu, double dt, double dx, double tol, int shape)

@@ -3,8 +3,8 @@
 // There is no GPU in the build container, so the index logic AND the synchronisation protocol of
 // the pass (csrc/syst_pass_body.cuh) are exercised here by compiling the very same per-thread code
 // for the host and running every lane of a thread block as a real thread:
-//   * mbarriers are atomics with the hardware's phase-parity semantics (a waiter that falls a whole
-//     ring of progress slots behind would hang exactly as on the device);
+//   * the progress counters are atomics with release / acquire ordering, the TMA full barriers atomics with
+//     the hardware's phase-parity semantics;
 //   * the TMA engine and the bulk-store engine are memcpy in the issuing thread;
 //   * shared memory starts as NaN, so a read of a cell that was never staged poisons the result;
 //   * built with -fsanitize=thread (tests/test_syst_pass_emu.py does both builds), every pair of
@@ -51,7 +51,7 @@ static pthread_barrier_t g_wbar[WARPS];
 // mbarrier model: completed-phase count; arrival count 1 (+ transaction bytes for the full barriers)
 struct MBar { std::atomic<unsigned long> phases{0}; std::atomic<long> tx{0}; };
 static MBar g_full[NGROUP];
-static MBar g_pb[NSTAGE * PBSLOTS];
+static std::atomic<unsigned> g_prog[NSTAGE];       // steps completed per stage warp
 static std::atomic<long> g_spins{0};
 static int g_jitter = 0;
 
@@ -110,13 +110,31 @@ SY_FN void sy_tma_load(const Params& p, const Smem& sm, int which, unsigned soff
 }
 SY_FN void sy_tma_prefetch(const Params&, int, int, int) {}
 SY_FN void sy_full_wait(const Smem&, int g, unsigned parity) { jitter(); mbar_wait(g_full[g], parity, "TMA group slot", g); }
-SY_FN void sy_pb_arrive(const Smem&, int warp, int slot)
+SY_FN void sy_prog_publish(const Smem&, int warp, unsigned steps_done)
 {
     jitter();
-    g_done[warp].fetch_add(1, std::memory_order_relaxed);
-    g_pb[warp * PBSLOTS + slot].phases.fetch_add(1, std::memory_order_release);
+    g_done[warp].store((long)steps_done, std::memory_order_relaxed);
+    g_prog[warp].store(steps_done, std::memory_order_release);
 }
-SY_FN void sy_pb_wait(const Smem&, int warp, int slot, unsigned parity) { jitter(); mbar_wait(g_pb[warp * PBSLOTS + slot], parity, "warp", warp * 1000 + slot); }
+SY_FN Prog2 sy_prog_peek(const Smem&, int stage)
+{
+    jitter();
+    Prog2 v;
+    v.h0 = g_prog[2 * stage].load(std::memory_order_acquire);
+    v.h1 = g_prog[2 * stage + 1].load(std::memory_order_acquire);
+    return v;
+}
+SY_FN void sy_backoff()
+{
+    static thread_local long spins = 0;
+    sched_yield();
+    if (++spins % 3000000L == 0) {                        // a protocol deadlock: die loudly instead of hanging the suite
+        std::fprintf(stderr, "syst_emu: warp %d lane %d has been spinning on a progress counter; steps published:", t_warp, t_lane);
+        for (int w = 0; w < NSTAGE; ++w) std::fprintf(stderr, " %ld", g_done[w].load());
+        std::fprintf(stderr, "\n");
+        std::abort();
+    }
+}
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes) { std::memcpy(gdst, sm.raw + soff, bytes); }
 SY_FN void sy_store_commit() {}
 SY_FN void sy_store_wait_read0() {}
@@ -192,7 +210,7 @@ long syst_emu_run(long n, long pitch, long odd, long cpitch, long codd, const do
         double* sd = reinterpret_cast<double*>(sbase);
         for (size_t q = 0; q < SMEM_BYTES / 8; ++q) sd[q] = std::numeric_limits<double>::quiet_NaN();
         for (auto& b : g_full) { b.phases.store(0); b.tx.store(0); }
-        for (auto& b : g_pb) { b.phases.store(0); b.tx.store(0); }
+        for (auto& c : g_prog) c.store(0);
         for (auto& d : g_done) d.store(0);
         Smem sm;
         carve(sm, sbase, p.SWK);

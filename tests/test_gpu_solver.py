@@ -150,6 +150,25 @@ def test_fused_equals_unfused_bitwise(mg, oracle):
         assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=0)
 
 
+@pytest.mark.skipif("fused" not in PLANS or "unfused" not in PLANS, reason="needs both plans")
+@pytest.mark.parametrize("niter", [0, 1, 2, 4, 5, 7])
+def test_smoothing_counts_other_than_the_reference_default(mg, niter):
+    """options.niter != 3 (the reference hard-codes NITER = 3, multigrid.cpp:41): the fused plan cuts the sweeps into
+    passes of at most three iterations (4 = 3+1, 7 = 3+3+1) and must equal the one-operator plan bit for bit;
+    niter = 0 has nothing to fuse and runs the one-operator plan"""
+    n = 256; dx = 1.0 / n; dt = dx / 10
+    res = []
+    for plan in (mg.PLAN_UNFUSED, mg.PLAN_FUSED):
+        with mg.Solver(n, -4e-4, dt, dx, 1e-12, shape=1, arith=mg.ARITH_EXACT, plan=plan, niter=niter) as s:
+            s.set_fields_reference_ic(2.0)
+            s.form_rhs()
+            norms = [s.cycle() for _ in range(2)]
+            res.append(([s.level(l, "u") for l in range(s.maxlvl)], norms))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert np.array_equal(a, b)
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=0)
+
+
 def test_full_weighting_option(mg, oracle):
     """options.restriction = 1 (opt-in, UNFUSED plan): converges to the same solution as the reference's
     injection; rejected on the fused plan"""
