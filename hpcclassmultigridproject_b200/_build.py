@@ -49,20 +49,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_experimental(verbose: bool = False) -> str:
-    """csrc/experimental/wasp_pass.cu -> libmgb200x.so: the next-round kernel candidate, a library of
-    its own (never linked into or loaded by the product)."""
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    src = os.path.join(CSRC, "experimental", "wasp_pass.cu")
-    out = os.path.join(CSRC, "experimental", "libmgb200x.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", out, src]
-    if verbose:
-        print(" ".join(cmd))
-    env = dict(os.environ)
-    env.pop("CC", None); env.pop("CXX", None)
-    subprocess.run(cmd, check=True, env=env)
-    return out
-
-
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

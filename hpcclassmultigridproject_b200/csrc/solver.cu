@@ -5,7 +5,7 @@
 // split layout (common.cuh).  Two pass plans produce the same field:
 //   UNFUSED  one launch per reference operator (ops_basic.cu): 2 launches per RB iteration,
 //            residual, injection, zero, prolong+add.   W = 320 B/node/level.
-//   FUSED    one streaming launch per leg (stream_pass.cu): {3 RB iterations + residual +
+//   FUSED    one streaming launch per leg (syst_pass.cu): {3 RB iterations + residual +
 //            injection} going down, {prolong + correct + 3 RB iterations (+ residual norm on
 //            level 0)} coming up.                      W = 84 B/node/level.
 // One whole cycle + convergence check is captured into a CUDA graph and replayed; the only

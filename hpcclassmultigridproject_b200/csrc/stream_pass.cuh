@@ -1,4 +1,5 @@
-// stream_pass.cuh -- interface of the fused streaming kernel (definition: stream_pass.cu).
+// stream_pass.cuh -- interface of the fused streaming kernel (definition: syst_pass.cu, per-thread logic:
+// syst_pass_body.cuh).
 //
 // One launch = one "pass" over one level in the solver's split layout:
 //     [u += P(coarse u)]  ->  K red-black Gauss-Seidel iterations  ->  [residual epilogue]
@@ -24,7 +25,7 @@ struct StreamPassArgs {
     const double* rhs;
     const double* v1;
     const double* v2;
-    int iters;              // K in [0,3]
+    int iters;              // K in [1,3]
     // optional prologue: u += P(coarse)
     const double* coarse_u; // null = none
     Layout Lc;              // layout of the (n/2) level
@@ -40,15 +41,10 @@ struct StreamPassArgs {
 };
 
 // number of tiles (= partial sums written by POST_NORM2) of a pass over level n with `iters`
-// fused iterations; iters < 0: the maximum over all iteration counts (buffer sizing)
+// fused iterations; iters < 1: the maximum over all iteration counts (buffer sizing)
 long stream_pass_tiles(long n, long nrows, int iters);
 // one-time attribute setup
 int stream_pass_init();
 int stream_pass(const StreamPassArgs& a, cudaStream_t s);
-
-// the systolic implementation of the same pass (syst_pass.cu): iters >= 1 only
-int syst_pass_init();
-long syst_pass_tiles(long n, long nrows, int iters);
-int syst_pass(const StreamPassArgs& a, cudaStream_t s);
 
 }  // namespace mgb200

@@ -81,14 +81,9 @@ SY_FN Prog2 sy_prog_peek(const Smem& sm, int stage)
     return v;
 }
 
-#ifndef MGB200_SY_BACKOFF_NS
-#define MGB200_SY_BACKOFF_NS 0
-#endif
-SY_FN void sy_backoff()
+SY_FN void sy_backoff(int ns)
 {
-#if MGB200_SY_BACKOFF_NS > 0
-    __nanosleep(MGB200_SY_BACKOFF_NS);
-#endif
+    if (ns > 0) __nanosleep((unsigned)ns);
 }
 
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes)
@@ -220,7 +215,7 @@ static PassKernel pass_kernel(int arith, bool pre, int post)
 using namespace sy;
 
 // per-device set-up (function attributes are per device)
-int syst_pass_init()
+int stream_pass_init()
 {
     static std::mutex mu;
     static bool done[64] = {};
@@ -244,7 +239,7 @@ int syst_pass_init()
     return MGB200_OK;
 }
 
-long syst_pass_tiles(long n, long nrows, int iters)
+long stream_pass_tiles(long n, long nrows, int iters)
 {
     if (iters >= 1) {
         const Plan pl = plan_for(n, nrows, iters > KMAX ? KMAX : iters);
@@ -260,10 +255,10 @@ long syst_pass_tiles(long n, long nrows, int iters)
 
 static int build_params(const StreamPassArgs& a, Params& p, unsigned& grid_out, size_t& smem_out)
 {
-    if (a.iters < 1 || a.iters > KMAX) return fail(MGB200_ERR_INVALID, "syst_pass: iters must be 1..3");
-    if (a.n < 8 || (a.n & 3)) return fail(MGB200_ERR_INVALID, "syst_pass: n must be a multiple of 4, >= 8");
-    if (!a.L.split() || a.u_out == a.u_in) return fail(MGB200_ERR_INVALID, "syst_pass: needs the split layout and u_out != u_in");
-    MGB_TRY(syst_pass_init());
+    if (a.iters < 1 || a.iters > KMAX) return fail(MGB200_ERR_INVALID, "stream_pass: iters must be 1..3");
+    if (a.n < 8 || (a.n & 3)) return fail(MGB200_ERR_INVALID, "stream_pass: n must be a multiple of 4, >= 8");
+    if (!a.L.split() || a.u_out == a.u_in) return fail(MGB200_ERR_INVALID, "stream_pass: needs the split layout and u_out != u_in");
+    MGB_TRY(stream_pass_init());
     const bool whole = a.rows_mem == 0;
     const long own_lo = whole ? 0 : a.own_lo, own_hi = whole ? a.n : a.own_hi;
     const Plan pl = plan_for(a.n, own_hi - own_lo + 1, a.iters);
@@ -281,6 +276,7 @@ static int build_params(const StreamPassArgs& a, Params& p, unsigned& grid_out, 
     p.post = a.post;
     p.u_is_zero = a.u_in ? 0 : 1;
     p.CW = pl.SWK / 2 + 8;
+    { const char* e = getenv("MGB200_SY_BACKOFF"); p.backoff_ns = e ? atoi(e) : 0; }   // tuning aid
     p.st = a.st;
     p.u_in = a.u_in; p.rhs = a.rhs; p.v1 = a.v1; p.v2 = a.v2; p.cu = a.coarse_u;
     // the u map of a zero-input pass is never dereferenced (its boxes lie out of bounds): any valid field will do
@@ -290,14 +286,14 @@ static int build_params(const StreamPassArgs& a, Params& p, unsigned& grid_out, 
     MGB_TRY(encode_field(&p.maps[FIELD_V2], a.v2, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
     if (a.coarse_u) MGB_TRY(encode_field(&p.maps[FIELD_C], a.coarse_u, a.Lc.odd, a.Lc.pitch, p.crows_mem, p.CW, CROWS));
     p.u_out = a.u_out; p.crhs = a.coarse_rhs; p.partials = a.partials;
-    if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "syst_pass: POST_INJECT without coarse_rhs");
-    if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "syst_pass: POST_NORM2 without partials");
+    if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "stream_pass: POST_INJECT without coarse_rhs");
+    if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "stream_pass: POST_NORM2 without partials");
     grid_out = (unsigned)(pl.nstrips * pl.nbands);
     smem_out = smem_bytes(pl.SWK);
     return MGB200_OK;
 }
 
-int syst_pass(const StreamPassArgs& a, cudaStream_t s)
+int stream_pass(const StreamPassArgs& a, cudaStream_t s)
 {
     // The kernel parameter block (five encoded tensor maps, the tile plan, the row window) depends
     // only on the argument record: a solver issues the same few dozen passes every cycle, so blocks

@@ -83,6 +83,7 @@ struct Params {
     int post;                  // StreamPost
     int u_is_zero;             // u_in == 0 everywhere: rows are zero-filled by an out-of-bounds box
     int CW;                    // SWK/2 + 8: coarse pairs per smem run
+    int backoff_ns;            // pause between two unsuccessful looks at a progress counter (0: none)
     Stencil st;
     const double* u_in;
     const double* rhs;
@@ -161,7 +162,7 @@ SY_FN void sy_full_wait(const Smem& sm, int g, unsigned parity);
 struct Prog2 { unsigned h0, h1; };
 SY_FN void sy_prog_publish(const Smem& sm, int warp, unsigned steps_done);
 SY_FN Prog2 sy_prog_peek(const Smem& sm, int stage);
-SY_FN void sy_backoff();                                 // between two unsuccessful peeks
+SY_FN void sy_backoff(int ns);                           // between two unsuccessful peeks
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes);
 SY_FN void sy_store_commit();
 SY_FN void sy_store_wait_read0();                        // every committed store has read its shared memory
@@ -187,6 +188,7 @@ struct Geo {
     unsigned cwb;     // bytes of one coarse parity run
     unsigned cgrpb;   // bytes of the coarse rows of one group
     int nh;           // warps per stage that hold live pairs (1 for strips of <= 64 pairs)
+    int backoff_ns;
 };
 SY_FN Geo make_geo(const Params& p)
 {
@@ -194,6 +196,7 @@ SY_FN Geo make_geo(const Params& p)
     g.swkb = (unsigned)p.SWK * 8u; g.rowb = 2u * g.swkb; g.ringb = (unsigned)RING * g.rowb;
     g.cwb = (unsigned)p.CW * 8u; g.cgrpb = (unsigned)CROWS * 2u * g.cwb;
     g.nh = p.SWK > 64 ? 2 : 1;
+    g.backoff_ns = p.backoff_ns;
     return g;
 }
 
@@ -294,9 +297,9 @@ SY_FN void advance_row(const Geo& geo, Stage& st)
 }
 
 // wait until the warps of pair `pair` have completed `need0` / `need1` steps (pv: a peek taken earlier)
-SY_FN void prog_wait(const Smem& sm, int pair, unsigned need0, unsigned need1, Prog2 pv)
+SY_FN void prog_wait(const Smem& sm, int pair, unsigned need0, unsigned need1, Prog2 pv, int backoff_ns = 0)
 {
-    while (pv.h0 < need0 || pv.h1 < need1) { sy_backoff(); pv = sy_prog_peek(sm, pair); }
+    while (pv.h0 < need0 || pv.h1 < need1) { sy_backoff(backoff_ns); pv = sy_prog_peek(sm, pair); }
 }
 
 // wait for the data of step k: the TMA group of row t (roles fed by the TMA engine) or step k-1 of the role above
@@ -309,7 +312,7 @@ SY_FN void wait_inputs(const Tile& tl, const Geo& geo, const Smem& sm, const Sta
             sy_full_wait(sm, g % NGROUP, (unsigned)(g / NGROUP) & 1u);
         }
     } else {
-        prog_wait(sm, st.up, (unsigned)k, geo.nh == 2 ? (unsigned)k : 0u, seen);
+        prog_wait(sm, st.up, (unsigned)k, geo.nh == 2 ? (unsigned)k : 0u, seen, geo.backoff_ns);
     }
 }
 
@@ -335,7 +338,10 @@ SY_FN void pre_step(const Params& p, const Tile& tl, const Geo& geo, const Smem&
         const int crow = (t >> 1) - (G0 >> 1);                       // 0..2; an odd fine row also uses crow+1
         const unsigned c0 = 4u * geo.ringb + (unsigned)(g % NGROUP) * geo.cgrpb + (unsigned)crow * 2u * geo.cwb + (unsigned)(st.kk >> 1) * 8u;
         D2 u{0.0, 0.0};
-        if (st.live) u = sy_lds2(sm, a);
+#ifdef SY_HOST_MODEL
+        if (st.live)
+#endif
+        u = sy_lds2(sm, a);
         const double a0 = sy_lds1(sm, c0), a1 = sy_lds1(sm, c0 + geo.cwb);
         D2 e;
         if (PAR) {                                                   // even row, odd columns (gs.cpp:240)
@@ -373,7 +379,10 @@ SY_FN void pre_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem&
 //   RESID   nothing is updated: the residual of the nodes is injected (EPI = POST_INJECT: even columns of even
 //           rows) or squared and summed (POST_NORM2)
 //   CHECKED the step may touch rows outside [R0, R1] (first and last steps of a tile): their loads are skipped
-template <int ARITH, bool LAST, bool NORM1, bool RESID, int EPI>
+//   FULL    steady state of a strip that touches neither side of the domain: the update is active and every lane
+//           stores (the strip's outermost pairs are halo: what is computed there is never used), so the step
+//           carries no mask, no range test and no predicated load
+template <int ARITH, bool LAST, bool NORM1, bool RESID, int EPI, bool FULL>
 SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm, Stage& st, const int k, const int PAR,
                       const bool CHECKED)
 {
@@ -384,6 +393,11 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
     // must not load what that lane is storing)
     const bool own_ok = !CHECKED || (row >= tl.R0 && row <= tl.R1);
     const bool dn_ok = !CHECKED || (row + 1 >= tl.R0 && row + 1 <= tl.R1);
+#ifdef SY_HOST_MODEL
+    const bool live = st.live;       // (the race detector of the host model would flag the shadow lanes' loads)
+#else
+    const bool live = true;          // on the device a duplicate load is harmless and cheaper than a predicate
+#endif
     // ---- first look at the counters this step depends on: issued before the step's own loads, so that in the
     // steady state the answer is there when it is needed
     Prog2 seen{0u, 0u};
@@ -393,7 +407,7 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
     D2 f{0.0, 0.0}, w1{0.0, 0.0}, w2{0.0, 0.0}, own{0.0, 0.0};
     double x = 0.0;
     const D2 up = st.c_up, m = st.c_mid;
-    if (work && own_ok && st.live) {
+    if (work && own_ok && live) {
         f = sy_lds2(sm, c + geo.ringb); w1 = sy_lds2(sm, c + 2u * geo.ringb); w2 = sy_lds2(sm, c + 3u * geo.ringb);
         if (RESID) own = sy_lds2(sm, c);
     }
@@ -407,13 +421,13 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
     wait_inputs(tl, geo, sm, st, k, seen);
     // ---- after the wait
     D2 dn{0.0, 0.0};
-    if (dn_ok && st.live) dn = sy_lds2(sm, st.a_next + po);
+    if (dn_ok && live) dn = sy_lds2(sm, st.a_next + po);
     const unsigned rm = PAR ? st.rmask1 : st.rmask0;
     if (!RESID) {
         const double o0 = Arith<ARITH>::gs_tail(h0, dn.x, n1, c0.d, c0.b, p.st);
         const double o1 = Arith<ARITH>::gs_tail(h1, dn.y, n2, c1.d, c1.b, p.st);
-        const bool act = row >= st.lo && row <= st.hi;
-        const unsigned okb = act ? (PAR ? st.okp1 : st.okp0) : 0u;
+        const bool act = FULL || (row >= st.lo && row <= st.hi);
+        const unsigned okb = FULL ? 3u : act ? (PAR ? st.okp1 : st.okp0) : 0u;
         // one 16-byte store in the common case: two 8-byte stores at a 16-byte lane stride cost twice the wavefronts
         if (okb == 3u) sy_sts2(sm, c, D2{o0, o1});
         else {
@@ -459,18 +473,28 @@ SY_FN void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Sme
     int par = (st.s + st.row) & 1;
     int k = 0;
     // first steps: rows above R0 (checked); then align the unrolled loop on parity 0; last steps: rows below R1
-    // (checked: the slots of unstaged rows may still be in use by the roles behind)
-    const int kchk = st.off;                             // first step with row >= R0
-    int kmain = tl.R1 - tl.R0 + st.off - 1;              // last step with row + 1 <= R1
+    // (checked: the slots of unstaged rows may still be in use by the roles behind).  Unchecked steps: the update
+    // is active (row in [R0+1, R1-1]), hence rows row-1 .. row+1 staged.
+    const int kchk = st.off + 1;
+    int kmain = tl.R1 - tl.R0 + st.off - 1;
     if (kmain > klast) kmain = klast;
+    // a strip that touches neither side of the domain runs the mask-free step (every lane must be live)
+    const bool full = !RESID && tl.k0 >= 1 && (long)tl.k0 + p.SWK <= p.nhalf && (p.SWK & 63) == 0;
     for (; k <= klast && (k < kchk || par != 0); ++k, par ^= 1)
-        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, par, true);
-    for (; k + 1 <= kmain; k += 2) {
-        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, 0, false);
-        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k + 1, 1, false);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI, false>(p, tl, geo, sm, st, k, par, true);
+    if (full) {
+        for (; k + 1 <= kmain; k += 2) {
+            stage_step<ARITH, LAST, NORM1, RESID, EPI, true>(p, tl, geo, sm, st, k, 0, false);
+            stage_step<ARITH, LAST, NORM1, RESID, EPI, true>(p, tl, geo, sm, st, k + 1, 1, false);
+        }
+    } else {
+        for (; k + 1 <= kmain; k += 2) {
+            stage_step<ARITH, LAST, NORM1, RESID, EPI, false>(p, tl, geo, sm, st, k, 0, false);
+            stage_step<ARITH, LAST, NORM1, RESID, EPI, false>(p, tl, geo, sm, st, k + 1, 1, false);
+        }
     }
     for (; k <= klast; ++k, par ^= 1)
-        stage_step<ARITH, LAST, NORM1, RESID, EPI>(p, tl, geo, sm, st, k, par, true);
+        stage_step<ARITH, LAST, NORM1, RESID, EPI, false>(p, tl, geo, sm, st, k, par, true);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -124,7 +124,7 @@ SY_FN Prog2 sy_prog_peek(const Smem&, int stage)
     v.h1 = g_prog[2 * stage + 1].load(std::memory_order_acquire);
     return v;
 }
-SY_FN void sy_backoff()
+SY_FN void sy_backoff(int)
 {
     static thread_local long spins = 0;
     sched_yield();

@@ -37,6 +37,7 @@ int main()
         {288, 3, 1, 1, 120, 2, 4},    // two warps per stage: strip-half edges, prolongation + injection
         {288, 3, 2, 1, 120, 1, 0},    // ... with the norm
         {288, 3, 0, 0, 88, 3, 8},     // a partially filled second half
+        {512, 3, 1, 1, 120, 4, 2},    // interior strips: the mask-free step
     };
     for (const Case& c : cases) {
         const long n = c.n, odd = lay_odd(n), pitch = 2 * odd, codd = lay_odd(n / 2), cpitch = 2 * codd;

@@ -53,13 +53,11 @@ def _worker(rank, world, port, n, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import ctypes as C
     import hpcclassmultigridproject_b200 as mg
-    import test_stream_pass_emu as T
+    import emu_util as T
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import torch
-    emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "libspemu.so"))
-    emu.sp_emu_run.restype = C.c_long
-    emu.sp_emu_run.argtypes = [C.c_long] * 5 + [T._dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_long] * 6
+    emu = T.load_model()
 
     maxlvl = 3
     w = mg.slab_plan(n, maxlvl, world, rank, 0, 16)
@@ -79,7 +77,7 @@ def _worker(rank, world, port, n, out_dir):
         out = np.full((w["mem_hi"] - w["mem_lo"] + 1, pitch), np.nan)
         crhs = np.zeros((wc["mem_hi"] - wc["mem_lo"] + 1, cp))
         parts = np.zeros(4096)
-        nt = emu.sp_emu_run(n, pitch, odd, cp, co, T.ptr(u_in), T.ptr(out), T.ptr(window(rhs)), T.ptr(window(v1)),
+        nt = emu.syst_emu_run(n, pitch, odd, cp, co, T.ptr(u_in), T.ptr(out), T.ptr(window(rhs)), T.ptr(window(v1)),
                             T.ptr(window(v2)), T.ptr(coarse_u), T.ptr(crhs), T.ptr(parts), K, post, 1, dt, nu, dx, 0, 0, rank,
                             w["own_lo"], w["own_hi"], w["mem_lo"], out.shape[0], wc["mem_lo"], crhs.shape[0])
         assert nt > 0
@@ -120,14 +118,8 @@ def _worker(rank, world, port, n, out_dir):
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_ranks_reproduce_the_unsharded_pass_gloo(oracle, tmp_path, world):
     import torch.multiprocessing as mp
-    import test_stream_pass_emu as T
-    from test_stream_pass_emu import emu as _  # noqa: F401  (builds libspemu.so through the fixture below)
-    import subprocess
-    so = os.path.join(ROOT, "tests", "emu", "libspemu.so")
-    src = os.path.join(ROOT, "tests", "emu", "sp_emu.cpp")
-    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-I/usr/local/cuda/include",
-                        "-o", so, src], check=True)
+    import emu_util as T
+    T.load_model()                      # built once here, loaded by the ranks
     n = 256
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)

@@ -4,41 +4,18 @@ with the hardware's mbarrier semantics) against the oracle: ring / pipeline / ha
 the barrier protocol, checked bit-for-bit with NaN-poisoned shared memory; a ThreadSanitizer build
 of the same model reports every pair of conflicting shared-memory accesses the protocol leaves
 unordered."""
-import ctypes as C
 import os
 import subprocess
 
 import numpy as np
 import pytest
 
-from conftest import ROOT
-from test_stream_pass_emu import fields, from_split, layout, ptr, to_split
-
-EMU_DIR = os.path.join(ROOT, "tests", "emu")
-_dp = C.POINTER(C.c_double)
-SRC = [os.path.join(EMU_DIR, "syst_emu.cpp"),
-       os.path.join(ROOT, "hpcclassmultigridproject_b200", "csrc", "syst_pass_body.cuh"),
-       os.path.join(ROOT, "hpcclassmultigridproject_b200", "csrc", "common.cuh")]
-
-
-def _env():
-    return {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-
-
-def _stale(out):
-    return not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in SRC)
+from emu_util import EMU_DIR, SRC, env_without_cc, fields, from_split, layout, load_model, ptr, stale, to_split
 
 
 @pytest.fixture(scope="module")
 def emu():
-    so = os.path.join(EMU_DIR, "libsystemu.so")
-    if _stale(so):
-        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-pthread",
-                        "-I/usr/local/cuda/include", "-o", so, SRC[0]], check=True, env=_env())
-    lib = C.CDLL(so)
-    lib.syst_emu_run.restype = C.c_long
-    lib.syst_emu_run.argtypes = [C.c_long] * 5 + [_dp] * 8 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_long] * 6
-    return lib
+    return load_model()
 
 
 def run(emu, n, u, rhs, v1, v2, K, post, arith, dt, nu, dx, cu=None, wk=0, nbands=0, jitter=0):
@@ -108,6 +85,28 @@ def test_plain_smoothing_zero_input_and_fast_arithmetic(emu, oracle):
     assert np.array_equal(got2, want2) and not crhs.any() and not parts.any()
 
 
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("wk,nb", [(56, 3), (120, 2)])
+def test_interior_strips_run_the_mask_free_step(emu, oracle, wk, nb):
+    """n = 512: the middle strips touch neither side of the domain and run the step without masks (every lane stores,
+    the strip's outermost pairs hold halo garbage); both legs must still equal the oracle bit for bit"""
+    n = 512
+    u, rhs, v1, v2 = fields(n, 77)
+    cu = np.random.default_rng(8).standard_normal((n // 2 + 1, n // 2 + 1))
+    cu[0, :] = cu[-1, :] = 0; cu[:, 0] = cu[:, -1] = 0
+    dx = 1.0 / n; dt = dx / 10; nu = -4e-4
+    want_u = oracle.gauss_seidel(u.copy(), rhs, n, v1, v2, dt, nu, dx, 3)
+    want_c = oracle.restriction(oracle.residual(want_u, rhs, n, v1, v2, dt, nu, dx), n)
+    got_u, got_c, _ = run(emu, n, u, rhs, v1, v2, 3, 1, 1, dt, nu, dx, wk=wk, nbands=nb, jitter=2)
+    assert np.array_equal(got_u, want_u)
+    assert np.array_equal(got_c[1:-1, 1:-1], want_c[1:-1, 1:-1])
+    want_u = oracle.gauss_seidel(u + oracle.prolongation(cu, n // 2), rhs, n, v1, v2, dt, nu, dx, 3)
+    want_r2 = oracle.norm(oracle.residual(want_u, rhs, n, v1, v2, dt, nu, dx), n) ** 2
+    got_u, _, parts = run(emu, n, u, rhs, v1, v2, 3, 2, 1, dt, nu, dx, cu=cu, wk=wk, nbands=nb, jitter=0)
+    assert np.array_equal(got_u, want_u)
+    assert abs(parts.sum() - want_r2) <= 1e-12 * want_r2
+
+
 @pytest.mark.timeout(900)
 def test_pre_with_injection(emu, oracle):
     """an up-leg chunk that is followed by nothing (W-cycle inner repetitions): prolongation + smoothing + injection"""
@@ -171,11 +170,11 @@ def test_barrier_protocol_under_thread_sanitizer():
     (both legs, K = 1..3, one and two warps per stage, several bands): no unordered conflicting access."""
     exe = os.path.join(EMU_DIR, "syst_tsan")
     main = os.path.join(EMU_DIR, "syst_tsan_main.cpp")
-    if _stale(exe) or os.path.getmtime(main) > os.path.getmtime(exe):
+    if stale(exe, [main]):
         r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-std=c++17", "-pthread",
-                            "-I/usr/local/cuda/include", "-o", exe, main, SRC[0]], capture_output=True, text=True, env=_env())
+                            "-I/usr/local/cuda/include", "-o", exe, main, SRC[0]], capture_output=True, text=True, env=env_without_cc())
         assert r.returncode == 0, r.stderr[-3000:]
-    env = dict(_env(), TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4")
+    env = dict(env_without_cc(), TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4")
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=1700)
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
