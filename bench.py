@@ -200,16 +200,14 @@ def parity_block(mg, s, n, rank, world, dist, arith_name):
     from hpcclassmultigridproject_b200 import digest
     s.set_fields_reference_ic(VSCALE)
     info = s.timestep(1)[0]
-    u = s.get_u_host()                                  # a slab rank fills its own rows, the rest stays NaN
-    sl = s.slab(0)
-    lo, hi = (sl["own_lo"], sl["own_hi"]) if world > 1 else (0, n)
+    lo, hi, u = s.get_u_host_rows()                     # the rows this rank owns (all rows on one GPU)
     st = max(1, n // 128)
     rows = [i for i in range(0, n + 1, st) if lo <= i <= hi]
     mine = {
-        "digests": digest.slab_digests(u, n, lo, hi) if n % digest.NSLAB == 0 else {},
-        "sumsq": float(np.sum(u[lo:hi + 1] * u[lo:hi + 1])),
-        "mid": float(u[n // 2, n // 2]) if lo <= n // 2 <= hi else None,
-        "sample_rows": rows, "sample": u[rows, ::st].copy(),
+        "digests": digest.slab_digests(u, n, lo, hi, base_row=lo) if n % digest.NSLAB == 0 else {},
+        "sumsq": float(np.einsum("ij,ij->", u, u)),
+        "mid": float(u[n // 2 - lo, n // 2]) if lo <= n // 2 <= hi else None,
+        "sample_rows": rows, "sample": u[[i - lo for i in rows], ::st].copy(),
     }
     del u
     parts = [mine]
@@ -354,43 +352,48 @@ def run_own(args, rank, world):
                 tt.append(el); cyc += info.cycles
         e2e = {"value": 1e3 * sum(tt) / max(1, cyc), "unit": "ms", "h2d_bytes_per_step": int(3 * m0 * 8),
                "d2h_bytes_per_step": int(m0 * 8), "call": "mgb200_timestepper_host (timestepper, multigrid.cpp:124), T=dt",
-               "ms_per_call": 1e3 * sum(tt) / len(tt), "cycles_per_call": cyc / len(tt)}
+               "ms_per_call": 1e3 * sum(tt) / len(tt), "cycles_per_call": cyc / len(tt),
+               "host_link_GBps": 4 * m0 * 8 / (sum(tt) / len(tt)) / 1e9,
+               "note": "copy-bound: (H2D + D2H bytes) / call time = host_link_GBps, per GPU"}
         mg.release_cached()
         del host
     elif not args.no_e2e:
         # sharded: the same sequence through the handle API, every rank moving its own row slab:
         # pinned host slab (+halo, + the rows the coarse-velocity towers read) -> device, one time
         # step, owned rows of the result -> pinned host
-        import numpy as np
-        rows = slice(slab["mem_lo"], slab["mem_hi"] + 1)
-        d = [torch.empty(n + 1, n + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
-        mg.ops.initial_conditions(*d, n, VSCALE)
-        host = [torch.empty(n + 1, n + 1, dtype=torch.float64).pin_memory() for _ in range(4)]
+        own_rows = slab["own_hi"] - slab["own_lo"] + 1
+        win_rows = slab["mem_hi"] - slab["mem_lo"] + 1
+        # each rank keeps ONLY its window of the inputs and its own rows of the result in (pinned) host memory
+        d = [torch.empty(win_rows, n + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
+        mg.ops.initial_conditions_rows(*d, n, VSCALE, slab["mem_lo"], slab["mem_hi"])
+        host = [torch.empty(win_rows, n + 1, dtype=torch.float64).pin_memory() for _ in range(3)]
         for h, t in zip(host, d):
             h.copy_(t)
         del d
+        out_rows = torch.empty(own_rows, n + 1, dtype=torch.float64).pin_memory()
         torch.cuda.synchronize(); torch.cuda.empty_cache()
         reps, tt, cyc = max(1, min(args.steps, 3)), [], 0
         for k in range(1 + reps):
             barrier()
             t0 = time.perf_counter()
-            s.set_fields_host(host[0], host[1], host[2])
+            s.set_fields_host_window(host[0], host[1], host[2])
             info = s.timestep(1)[0]
-            s.get_u_host(host[3])
+            s.get_u_host_rows(out_rows)
             barrier()
             el = time.perf_counter() - t0
             if k >= 1:
                 tt.append(el); cyc += info.cycles
         t = torch.tensor([sum(tt)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        own_rows = slab["own_hi"] - slab["own_lo"] + 1
-        win_rows = slab["mem_hi"] - slab["mem_lo"] + 1
         e2e = {"value": 1e3 * float(t.item()) / max(1, cyc), "unit": "ms",
-               "h2d_bytes_per_step": int(world * (3 * win_rows + 2 * (n // 4 + 2)) * (n + 1) * 8),
+               "h2d_bytes_per_step": int(world * 3 * win_rows * (n + 1) * 8),
                "d2h_bytes_per_step": int(m0 * 8),
                "call": "mgb200_set_fields_host + mgb200_timestep(1) + mgb200_get_u_host on every rank's slab",
-               "ms_per_call": 1e3 * float(t.item()) / len(tt), "cycles_per_call": cyc / len(tt)}
-        del host
+               "ms_per_call": 1e3 * float(t.item()) / len(tt), "cycles_per_call": cyc / len(tt),
+               "host_link_GBps": (3 * win_rows + own_rows) * (n + 1) * 8 / (float(t.item()) / len(tt)) / 1e9,
+               "note": "every rank moves its own slab over its own host link; the rows the coarse-velocity towers need "
+                       "travel once (owner -> peers over NVLink); host_link_GBps is per GPU"}
+        del host, out_rows
     if world > 1:
         s.close()
 

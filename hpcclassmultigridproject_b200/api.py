@@ -59,6 +59,7 @@ def lib():
     L.mgb200_vecadd.argtypes = [_vp, _vp, _vp, _l, _l, _vp]
     L.mgb200_restriction_fw.argtypes = L.mgb200_restriction.argtypes
     L.mgb200_initial_conditions.argtypes = [_vp, _vp, _vp, _l, _l, _d, _vp]
+    L.mgb200_initial_conditions_rows.argtypes = [_vp, _vp, _vp, _l, _l, _d, _l, _l, _vp]
     L.mgb200_default_options.argtypes = [C.POINTER(Options)]
     L.mgb200_default_options.restype = None
     L.mgb200_create.argtypes = [C.POINTER(_vp), _l, _i, _d, _d, _d, _d, C.POINTER(Options)]
@@ -189,6 +190,10 @@ class _Ops:
     def initial_conditions(self, u0, v1, v2, n, vscale=1.0, stream=None):
         _ck(lib().mgb200_initial_conditions(_ptr(u0), _ptr(v1), _ptr(v2), n, self._ld(u0), vscale, stream))
 
+    def initial_conditions_rows(self, u0, v1, v2, n, vscale, row_lo, row_hi, stream=None):
+        """rows row_lo..row_hi only; the tensors hold just those rows"""
+        _ck(lib().mgb200_initial_conditions_rows(_ptr(u0), _ptr(v1), _ptr(v2), n, self._ld(u0), vscale, row_lo, row_hi, stream))
+
 
 ops = _Ops()
 
@@ -276,6 +281,28 @@ class Solver:
             out = np.full((self.n + 1, self.n + 1), np.nan) if self.nranks > 1 else np.empty((self.n + 1, self.n + 1))
         _ck(lib().mgb200_get_u_host(self.h, _ptr(out)))
         return out
+
+    def set_fields_host_window(self, u0w, v1w, v2w):
+        """sharded handle: the arrays hold ONLY this rank's window, rows slab(0)['mem_lo'] .. ['mem_hi'] of the dense
+        (n+1)-wide fields (numpy or pinned torch CPU tensors).  mgb200_set_fields_host reads nothing outside the
+        window, so it is handed the address the full array WOULD start at."""
+        w = self.slab(0)
+        rows = w["mem_hi"] - w["mem_lo"] + 1
+        off = w["mem_lo"] * (self.n + 1) * 8
+        for a in (u0w, v1w, v2w):
+            assert tuple(a.shape) == (rows, self.n + 1), (tuple(a.shape), rows)
+        _ck(lib().mgb200_set_fields_host(self.h, _ptr(u0w) - off, _ptr(v1w) - off, _ptr(v2w) - off))
+
+    def get_u_host_rows(self, out=None):
+        """the rows this rank OWNS as an (own_hi - own_lo + 1) x (n+1) array (no full-size host array needed)"""
+        import numpy as np
+        w = self.slab(0)
+        lo, hi = (w["own_lo"], w["own_hi"]) if self.nranks > 1 else (0, self.n)
+        if out is None:
+            out = np.empty((hi - lo + 1, self.n + 1))
+        assert tuple(out.shape) == (hi - lo + 1, self.n + 1)
+        _ck(lib().mgb200_get_u_host(self.h, _ptr(out) - lo * (self.n + 1) * 8))
+        return lo, hi, out
 
     def get_u_device(self, out):
         _ck(lib().mgb200_get_u_device(self.h, _ptr(out), out.stride(0)))

@@ -135,4 +135,12 @@ int mgb200_initial_conditions(double* u0, double* v1, double* v2, long n, long l
     return launch_initial_conditions(u0, v1, v2, n, natural_layout(ld), vscale, (cudaStream_t)stream);
 }
 
+int mgb200_initial_conditions_rows(double* u0, double* v1, double* v2, long n, long ld, double vscale, long row_lo, long row_hi,
+                                   void* stream)
+{
+    if (!u0 || !v1 || !v2 || bad_grid(n, ld) || row_lo < 0 || row_hi > n || row_lo > row_hi)
+        return fail(MGB200_ERR_INVALID, "initial_conditions_rows: bad argument");
+    return launch_initial_conditions(u0, v1, v2, n, natural_layout(ld, row_lo), vscale, (cudaStream_t)stream, row_lo, row_hi);
+}
+
 }  // extern "C"

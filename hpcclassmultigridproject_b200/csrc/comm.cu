@@ -21,6 +21,7 @@ struct Nccl {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,6 +49,7 @@ int load_nccl()
     BIND(Recv, "ncclRecv");
     BIND(AllReduce, "ncclAllReduce");
     BIND(AllGather, "ncclAllGather");
+    BIND(Broadcast, "ncclBroadcast");
     BIND(GroupStart, "ncclGroupStart");
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
@@ -118,6 +120,13 @@ int comm_p2p(Comm* c, const P2P* ops, int nops, cudaStream_t s)
         else MGB_NCCL(g_nccl.Recv(o.buf, o.count, ncclFloat64, o.peer, c->nccl, s));
     }
     MGB_NCCL(g_nccl.GroupEnd());
+    return MGB200_OK;
+}
+
+int comm_broadcast(Comm* c, double* buf, size_t count, int root, cudaStream_t s)
+{
+    if (!c || c->nranks == 1 || count == 0) return MGB200_OK;
+    MGB_NCCL(g_nccl.Broadcast(buf, buf, count, ncclFloat64, root, c->nccl, s));
     return MGB200_OK;
 }
 

@@ -21,6 +21,8 @@ int comm_size(const Comm* c);
 // a batch of sends/receives issued as one NCCL group on `s`
 struct P2P { int peer; double* buf; size_t count; bool send; };
 int comm_p2p(Comm* c, const P2P* ops, int nops, cudaStream_t s);
+// `count` doubles from rank `root` to every rank, in place (set-up traffic over NVLink)
+int comm_broadcast(Comm* c, double* buf, size_t count, int root, cudaStream_t s);
 // in-place sum of `count` doubles on every rank
 int comm_allreduce_sum(Comm* c, double* buf, size_t count, cudaStream_t s);
 // every rank contributes `bytes` bytes (device memory); recv holds nranks * bytes

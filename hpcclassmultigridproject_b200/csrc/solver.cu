@@ -1164,20 +1164,33 @@ int mgb200_set_fields_host(mgb200_solver* s, const double* u0, const double* v1,
     double* stage_a = g.u[1 - g.cur];
     double* stage_b = g.rhs;
     const long before = launch_counter();
+    // Coarse-velocity towers of a sharded solver (P1): every rank needs rows 0..N/4+1 of the level-0 velocities.
+    // Each of those rows crosses PCIe ONCE, inside the window of the rank that owns it; the owner copies it from
+    // its staging area into the dense tower input and broadcasts it to the other ranks over NVLink.
+    const long top = s->N / 4 + 1;
+    auto towers_from_stage = [&](double* stage, double* dtop) -> int {
+        const long a = g.own_lo, b = g.own_hi < top ? g.own_hi : top;
+        if (a <= b)
+            MGB_CUDA(cudaMemcpyAsync(dtop + (size_t)a * (n + 1), stage + (size_t)(a - g.mem_lo) * (n + 1), (size_t)(b - a + 1) * (n + 1) * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, s->stream));
+        for (int r = 0; r < s->P; ++r) {
+            const Slab w = slab_of(g.n, s->P, r);
+            const long ra = w.own_lo, rb = w.own_hi < top ? w.own_hi : top;
+            if (ra <= rb) MGB_TRY(comm_broadcast(s->comm, dtop + (size_t)ra * (n + 1), (size_t)(rb - ra + 1) * (n + 1), r, s->stream));
+        }
+        return MGB200_OK;
+    };
+    if (s->P > 1) MGB_TRY(s->alloc_top());
     MGB_CUDA(cudaMemcpyAsync(stage_a, u0 + off, bytes, cudaMemcpyHostToDevice, s->stream));
     MGB_TRY(launch_convert(g.u[g.cur], g.L, stage_a, dense, n, s->stream, g.mem_lo, g.mem_hi));
     MGB_CUDA(cudaMemcpyAsync(stage_b, v1 + off, bytes, cudaMemcpyHostToDevice, s->stream));
     MGB_TRY(launch_convert(g.v1, g.L, stage_b, dense, n, s->stream, g.mem_lo, g.mem_hi));
+    if (s->P > 1) MGB_TRY(towers_from_stage(stage_b, s->d_top[1]));
     MGB_CUDA(cudaMemcpyAsync(stage_a, v2 + off, bytes, cudaMemcpyHostToDevice, s->stream));
     MGB_TRY(launch_convert(g.v2, g.L, stage_a, dense, n, s->stream, g.mem_lo, g.mem_hi));
+    if (s->P > 1) MGB_TRY(towers_from_stage(stage_a, s->d_top[2]));
     MGB_CUDA(cudaMemsetAsync(stage_a, 0, g.elems * sizeof(double), s->stream));
     MGB_CUDA(cudaMemsetAsync(stage_b, 0, g.elems * sizeof(double), s->stream));
-    if (s->P > 1) {
-        MGB_TRY(s->alloc_top());
-        const size_t tb = (size_t)(s->N / 4 + 2) * (n + 1) * sizeof(double);
-        MGB_CUDA(cudaMemcpyAsync(s->d_top[1], v1, tb, cudaMemcpyHostToDevice, s->stream));
-        MGB_CUDA(cudaMemcpyAsync(s->d_top[2], v2, tb, cudaMemcpyHostToDevice, s->stream));
-    }
     MGB_TRY(after_fields(s));
     s->count(before);
     MGB_CUDA(cudaStreamSynchronize(s->stream));

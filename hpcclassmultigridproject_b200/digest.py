@@ -21,18 +21,20 @@ def slab_rows(n: int, g: int):
     return g * per, (g + 1) * per - 1 + (1 if g == NSLAB - 1 else 0)
 
 
-def slab_digests(u, n: int, row_lo: int = 0, row_hi: int | None = None):
-    """{slab index: 32-byte digest} for the slabs lying inside rows row_lo..row_hi of the dense
-    float64 array `u` (numpy, shape (n+1, n+1), C order; rows outside [row_lo, row_hi] are not read)"""
+def slab_digests(u, n: int, row_lo: int = 0, row_hi: int | None = None, base_row: int = 0):
+    """{slab index: 32-byte digest} for the slabs lying inside rows row_lo..row_hi of the dense float64 field.
+    `u` (numpy, C order, n+1 columns) holds rows base_row .. base_row + len(u) - 1 of it: the whole field
+    (base_row = 0) or just the rows a rank owns."""
     import numpy as np
     row_hi = n if row_hi is None else row_hi
-    assert u.dtype == np.float64 and u.shape == (n + 1, n + 1) and u.flags.c_contiguous
+    assert u.dtype == np.float64 and u.ndim == 2 and u.shape[1] == n + 1 and u.flags.c_contiguous
+    assert base_row <= row_lo and row_hi <= base_row + u.shape[0] - 1
     assert n % NSLAB == 0
     out = {}
     for g in range(NSLAB):
         lo, hi = slab_rows(n, g)
         if lo >= row_lo and hi <= row_hi:
-            out[g] = hashlib.sha256(memoryview(u[lo:hi + 1]).cast("B")).digest()
+            out[g] = hashlib.sha256(memoryview(u[lo - base_row:hi + 1 - base_row]).cast("B")).digest()
     return out
 
 

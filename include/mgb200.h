@@ -109,6 +109,9 @@ int mgb200_vecadd(double *c, const double *a, const double *b, long n, long ld, 
  * Gaussian u0 with the boundary lines zeroed, vortex velocity scaled by vscale. */
 int mgb200_initial_conditions(double *u0, double *v1, double *v2, long n, long ld, double vscale,
                               void *stream);
+/* the same for rows row_lo..row_hi only: the arrays hold just those rows (row row_lo at offset 0) */
+int mgb200_initial_conditions_rows(double *u0, double *v1, double *v2, long n, long ld, double vscale,
+                                   long row_lo, long row_hi, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Solver handle: the V/W-cycle driver.  Replaces mg_inner / mg_outer / timestepper

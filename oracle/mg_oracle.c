@@ -226,6 +226,22 @@ orc_solver *orc_create(long n, int maxlvl, const double *u0, const double *v1,
     return s;
 }
 
+/* OPT-IN, no reference counterpart: replace the coarse velocity towers by TRUE injection,
+ * v_l[i][j] = v_{l-1}[2i][2j] with each level's own stride (what multigrid.cpp:148-160 presumably meant:
+ * the reference never halves n there, see above).  Pinned only to this formula -- which is plain
+ * subsampling, v_l = v_0[::2^l, ::2^l], checked as such in the tests. */
+void orc_correct_towers(orc_solver *s)
+{
+    for (int l = 1; l < s->maxlvl; ++l) {
+        const long nf = s->n >> (l - 1);
+        const size_t mh = (size_t)((s->n >> 1) + 1) * (size_t)((s->n >> 1) + 1);
+        memset(s->v1[l], 0, mh * sizeof(double));
+        memset(s->v2[l], 0, mh * sizeof(double));
+        orc_restriction(s->v1[l], s->v1[l - 1], nf);
+        orc_restriction(s->v2[l], s->v2[l - 1], nf);
+    }
+}
+
 void orc_destroy(orc_solver *s)
 {
     if (!s) return;

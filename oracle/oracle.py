@@ -73,6 +73,7 @@ class Oracle:
             L.orc_initial_conditions.argtypes = [_dp, _dp, _dp, l, d]
             L.orc_create.argtypes = [l, i, _dp, _dp, _dp, d, d, d, d, i]; L.orc_create.restype = C.c_void_p
             L.orc_destroy.argtypes = [C.c_void_p]
+            L.orc_correct_towers.argtypes = [C.c_void_p]
             L.orc_cycle.argtypes = [C.c_void_p, i]
             L.orc_form_rhs.argtypes = [C.c_void_p]
             L.orc_residual_norm.argtypes = [C.c_void_p]; L.orc_residual_norm.restype = d
@@ -216,12 +217,14 @@ class Towers:
 class OracleSolver:
     """orc_solver handle (mg_oracle.h) -- the restatement's driver with histories."""
 
-    def __init__(self, n, u0, v1, v2, nu, dt, dx, tol, shape=1, maxlvl=None):
+    def __init__(self, n, u0, v1, v2, nu, dt, dx, tol, shape=1, maxlvl=None, correct_towers=False):
         self.o = Oracle()
         self.n = n
         self.maxlvl = maxlvl_for(n) if maxlvl is None else maxlvl
         self.h = self.o.lib.orc_create(n, self.maxlvl, _p(u0), _p(v1), _p(v2), nu, dt, dx, tol, shape)
         assert self.h
+        if correct_towers:                # opt-in: true injection of the velocities (no reference twin)
+            self.o.lib.orc_correct_towers(self.h)
 
     def close(self):
         if self.h:

@@ -169,6 +169,37 @@ def test_smoothing_counts_other_than_the_reference_default(mg, niter):
     assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=0)
 
 
+@pytest.mark.parametrize("plan", PLANS)
+def test_corrected_velocity_towers_option(mg, oracle, plan):
+    """options.correct_towers = 1 (opt-in; the reference's towers, multigrid.cpp:148-160, never halve n): every coarse
+    velocity level is the plain subsampling of level 0, and the cycle equals the oracle's with the same towers bit for
+    bit; with the vortex of the reference the two tower variants give different coarse operators, hence different
+    iterates (so the option is not a no-op) but the same converged solution"""
+    n = 256; dx = 1.0 / n; dt = dx / 10; nu = -4e-4
+    u0, v1, v2 = oracle.initial_conditions(n, 3.0)
+    o = OracleSolver(n, u0, v1, v2, nu, dt, dx, 1e-12, 1, correct_towers=True)
+    with mg.Solver(n, nu, dt, dx, 1e-12, arith=mg.ARITH_EXACT, plan=plan_id(mg, plan), correct_towers=1) as s:
+        s.set_fields_host(u0, v1, v2)
+        for l in range(s.maxlvl):
+            assert np.array_equal(s.level(l, "v1"), v1[:: 1 << l, :: 1 << l]) and np.array_equal(s.level(l, "v2"), v2[:: 1 << l, :: 1 << l])
+            assert np.array_equal(o.v1(l), v1[:: 1 << l, :: 1 << l])
+        o.form_rhs(); s.form_rhs()
+        for _ in range(2):
+            o.cycle(); s.cycle()
+            for l in range(s.maxlvl):
+                assert np.array_equal(s.level(l, "u"), o.u(l)), l
+        corrected = s.get_u_host()
+    with mg.Solver(n, nu, dt, dx, 1e-12, arith=mg.ARITH_EXACT, plan=plan_id(mg, plan)) as s:
+        s.set_fields_host(u0, v1, v2)
+        s.form_rhs()
+        for _ in range(2):
+            s.cycle()
+        reference_towers = s.get_u_host()
+    assert not np.array_equal(corrected, reference_towers)
+    assert rel_l2(corrected, reference_towers) <= 1e-6          # two convergent iterations for the same fine-grid system
+    o.close()
+
+
 def test_full_weighting_option(mg, oracle):
     """options.restriction = 1 (opt-in, UNFUSED plan): converges to the same solution as the reference's
     injection; rejected on the fused plan"""
