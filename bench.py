@@ -323,7 +323,7 @@ def run_own(args, rank, world):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and n == N_FULL and world == 1:
         try:
-            traffic = json.load(open(tp)).get(f"{args.plan}_level0_bytes_per_launch")
+            traffic = json.load(open(tp)).get(f"{args.plan}_level0_bytes_per_launch")   # from the committed ncu capture (see "source" there)
         except Exception:
             traffic = None
     cycle_bytes = s.cycle_bytes
