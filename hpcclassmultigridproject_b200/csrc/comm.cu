@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(PUSH_TPB) k_peer_push(PeerPush a)
         const int slot = a.wait_slot[k];
         const int want = a.sync[8 + slot] + a.wait_count[k];
         int seen;
+        const long long t0 = clock64();
         do {
             asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(a.sync + slot) : "memory");
+            if (seen - want < 0 && clock64() - t0 > SYNC_SPIN_BUDGET) { a.sync[SYNC_ABORT] = 1; break; }   // the peer is gone
         } while (seen - want < 0);
         a.sync[8 + slot] = want;
     }
@@ -173,8 +175,10 @@ __device__ __forceinline__ void wait_arrivals(int* sync, int slot, int count)
 {
     const int want = sync[8 + slot] + count;
     int seen;
+    const long long t0 = clock64();
     do {
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sync + slot) : "memory");
+        if (seen - want < 0 && clock64() - t0 > SYNC_SPIN_BUDGET) { sync[SYNC_ABORT] = 1; break; }          // the peer is gone
     } while (seen - want < 0);
     sync[8 + slot] = want;
 }

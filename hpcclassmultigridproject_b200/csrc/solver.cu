@@ -179,6 +179,7 @@ struct mgb200_solver {
     int* d_sync = nullptr;             // this rank's counter block (layout: comm.cuh)
     double* d_red = nullptr;           // landing block of the norm reduction through rank 0
     int  allreduce_norm();             // d_norm2[0] <- sum over ranks
+    int  check_peers();                // after a synchronisation: did a device-side wait for a peer give up?
     std::vector<void*> ipc_mapped;
     int  setup_p2p();
     double* d_flat_scratch() { return d_norm2 + 4; }   // a spare double for set-up collectives
@@ -225,6 +226,8 @@ struct mgb200_solver {
     int  alloc_levels();
     int  alloc_top();
     void fill_pass_window(StreamPassArgs& a, const Level& g, const Level& c) const;
+    bool fused_push = false;           // halo rows stored into the neighbours by the passes themselves (peer memory only)
+    void fill_pass_push(StreamPassArgs& a, const Level& g, const Level& c, bool coarse_rhs_too) const;
     int  exchange_halo(Level& g, double* a, Level* g2 = nullptr, double* a2 = nullptr);
     int  gather_to_root(Level& c, double* arr);
     int  scatter_from_root(Level& c, double* arr);
@@ -379,6 +382,30 @@ void mgb200_solver::fill_pass_window(StreamPassArgs& a, const Level& g, const Le
     a.crow0 = c.mem_lo; a.crows_mem = c.rows_mem();
 }
 
+// Row slabs over peer memory: the pass itself stores the rows its neighbours need (its first / last SLAB_HALO rows of
+// the new iterate and, if the child level is sharded too, of the coarse right-hand side) into their halo rows and
+// raises their arrival counters when it ends; the neighbours' next pass waits for that in its edge tiles only.
+// One raise per pass and neighbour: every rank runs the same sequence of passes on the sharded levels, so "the
+// neighbour has finished as many passes as I have" is the whole protocol (comm.cuh, slots 6 / 7 / 17).
+void mgb200_solver::fill_pass_push(StreamPassArgs& a, const Level& g, const Level& c, bool coarse_rhs_too) const
+{
+    if (!(P > 1 && p2p && fused_push && g.sharded)) return;
+    const int l = (int)(&g - lv.data());
+    const int twin = a.u_out == g.u[0] ? 0 : 1;
+    a.sync = d_sync; a.push_rows = SLAB_HALO;
+    a.c_own_lo = c.own_lo; a.c_own_hi = c.own_hi;
+    for (int d = 0; d < 2; ++d) {
+        const int nb = d == 0 ? rank - 1 : rank + 1;
+        if (nb < 0 || nb >= P) continue;
+        const Slab w = slab_of(g.n, P, nb);
+        double* pu = peers[nb].lv[l].u[twin] - w.mem_lo * g.L.pitch;        // addressed by global row
+        double* pc = nullptr;
+        if (coarse_rhs_too && c.sharded) pc = peers[nb].lv[l + 1].rhs - slab_of(c.n, P, nb).mem_lo * c.L.pitch;
+        if (d == 0) { a.peer_u_up = pu; a.peer_c_up = pc; a.raise_up = peers[nb].sync + SYNC_PASS_DOWN; }   // we are its lower neighbour
+        else { a.peer_u_dn = pu; a.peer_c_dn = pc; a.raise_dn = peers[nb].sync + SYNC_PASS_UP; }
+    }
+}
+
 // Map the other ranks' arrays into this process (CUDA IPC over NVLink peer access): the slab
 // neighbours' u twins / rhs of every sharded level, and for the agglomeration step rank 0's coarse
 // rhs (on every rank) and every rank's coarse u (on rank 0).  All ranks agree on the outcome: if
@@ -449,12 +476,29 @@ int mgb200_solver::setup_p2p()
     MGB_CUDA(cudaMemcpyAsync(&flag, d_flat_scratch(), sizeof(double), cudaMemcpyDeviceToHost, stream));
     MGB_CUDA(cudaStreamSynchronize(stream));
     p2p = flag > P - 0.5;
+    // MGB200_FUSED_PUSH=1: the passes store their boundary rows into the neighbours themselves (fill_pass_push).
+    // Opt-in: measured at 2 and 8 GPUs it saves the eight exchange launches of a cycle but not the wait for the
+    // neighbour, which is what an exchange costs (profiles/README.md), and the replayed graph is 2-3 % slower with it.
+    { const char* f = getenv("MGB200_FUSED_PUSH"); fused_push = p2p && f && atoi(f) != 0; }
     if (!p2p) {
         for (void* m : ipc_mapped) cudaIpcCloseMemHandle(m);
         ipc_mapped.clear();
         peers.clear();
     }
     if (getenv("MGB200_TRACE") && rank == 0) fprintf(stderr, "MGB200_TRACE halo transport: %s\n", p2p ? "peer memory" : "nccl send/recv");
+    return MGB200_OK;
+}
+
+// The device-side waits for a peer (halo arrivals, gather / scatter, norm) give up after SYNC_SPIN_BUDGET ticks and
+// set a flag instead of spinning for ever when a rank has died or left the collective sequence; the host reads the
+// flag after it has synchronised and turns it into an error.
+int mgb200_solver::check_peers()
+{
+    if (P == 1 || !p2p || !d_sync) return MGB200_OK;
+    int flag = 0;
+    MGB_CUDA(cudaMemcpyAsync(&flag, d_sync + SYNC_ABORT, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    MGB_CUDA(cudaStreamSynchronize(stream));
+    if (flag) return fail(MGB200_ERR_STATE, "a peer rank did not arrive within the spin budget of a device-side wait (it failed or left the collective sequence); results are invalid");
     return MGB200_OK;
 }
 
@@ -700,17 +744,20 @@ int mgb200_solver::cycle_body(int l)
                 a.Lc = c.L;
                 if (left == 0) { a.post = POST_INJECT; a.coarse_rhs = c.rhs; }
                 fill_pass_window(a, g, c);
+                if (split) fill_pass_push(a, g, c, left == 0);
                 MGB_TRY(stream_pass(a, stream));
                 g.cur = 1 - g.cur;
                 first = false;
-                if (split && left > 0) MGB_TRY(exchange_halo(g, g.u[g.cur]));
+                if (split && left > 0 && !a.sync) MGB_TRY(exchange_halo(g, g.u[g.cur]));
             } while (left > 0);
             mark("L" + std::to_string(l) + "dn");
             if (split) {
-                // the new iterate's halo rows (read by the up leg) and the coarse right-hand side:
-                // halo rows to the slab neighbours, or everything to rank 0 if the child is agglomerated
-                if (c.sharded) MGB_TRY(exchange_halo(g, g.u[g.cur], &c, c.rhs));
-                else { MGB_TRY(exchange_halo(g, g.u[g.cur])); MGB_TRY(gather_to_root(c, c.rhs)); }
+                // the new iterate's halo rows (read by the up leg) and the coarse right-hand side: halo rows to the
+                // slab neighbours (stored by the pass itself over peer memory, else by an exchange), or everything
+                // to rank 0 if the child is agglomerated
+                const bool pushed = p2p && fused_push;
+                if (c.sharded) { if (!pushed) MGB_TRY(exchange_halo(g, g.u[g.cur], &c, c.rhs)); }
+                else { if (!pushed) MGB_TRY(exchange_halo(g, g.u[g.cur])); MGB_TRY(gather_to_root(c, c.rhs)); }
             }
             mark("L" + std::to_string(l) + "x");
             if (runs_level(l + 1)) MGB_TRY(cycle_body(l + 1));
@@ -731,11 +778,12 @@ int mgb200_solver::cycle_body(int l)
                 if (first) a.coarse_u = c.u[c.cur];
                 if (left == 0 && l == 0 && rep == opt.shape - 1) { a.post = POST_NORM2; a.partials = d_partials; }
                 fill_pass_window(a, g, c);
+                if (split) fill_pass_push(a, g, c, false);
                 MGB_TRY(stream_pass(a, stream));
                 g.cur = 1 - g.cur;
                 first = false;
                 mark("L" + std::to_string(l) + "up");
-                if (split) { MGB_TRY(exchange_halo(g, g.u[g.cur])); mark("L" + std::to_string(l) + "x"); }
+                if (split && !a.sync) { MGB_TRY(exchange_halo(g, g.u[g.cur])); mark("L" + std::to_string(l) + "x"); }
             } while (left > 0);
         }
     }
@@ -930,7 +978,7 @@ int mgb200_solver::solve(mgb200_solve_info* info)
             info->cycles = it; info->res0 = res0; info->res = res; info->converged = (res / res0 <= tol) ? 1 : 0;
         }
         if (rank == 0) report_solve(it, opt.max_cycle, res0, res, tol);
-        return MGB200_OK;
+        return check_peers();
     }
     if (!res0_on_host) {
         if (!norm_is_res0) return fail(MGB200_ERR_STATE, "solve: initial residual norm unknown; call form_rhs first");
@@ -998,7 +1046,7 @@ int mgb200_solver::timestep(int nsteps, mgb200_solve_info* infos)
         }
         if (rank == 0) report_solve(it, opt.max_cycle, res0, res, tol);
     }
-    return MGB200_OK;
+    return check_peers();
 }
 
 int mgb200_solver::get_u_natural(double* dst_dev, long ld)
@@ -1299,7 +1347,7 @@ int mgb200_synchronize(mgb200_solver* s)
 {
     if (!s) return fail(MGB200_ERR_INVALID, "solver == NULL");
     MGB_CUDA(cudaStreamSynchronize(s->stream));
-    return MGB200_OK;
+    return s->check_peers();
 }
 
 void* mgb200_stream(mgb200_solver* s) { return s ? (void*)s->stream : nullptr; }

@@ -11,6 +11,7 @@
 #include <string>
 #include <tuple>
 
+#include "comm.cuh"
 #include "syst_pass_body.cuh"
 
 namespace mgb200 {
@@ -86,6 +87,18 @@ SY_FN void sy_backoff(int ns)
     if (ns > 0) __nanosleep((unsigned)ns);
 }
 
+SY_FN void sy_wait_neighbour(int* sync, int slot)
+{
+    const int want = *reinterpret_cast<volatile int*>(sync + SYNC_PASSES_DONE);
+    int seen;
+    const long long t0 = clock64();
+    do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sync + slot) : "memory");
+        if (seen - want < 0 && clock64() - t0 > SYNC_SPIN_BUDGET) { sync[SYNC_ABORT] = 1; break; }   // the peer is gone
+    } while (seen - want < 0);
+    asm volatile("fence.proxy.async;" ::: "memory");   // the rows that arrived are read by the TMA engine
+}
+
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sm.base32 + soff), "r"(bytes) : "memory");
@@ -148,8 +161,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_syst_pass(const __grid_constant_
     if (threadIdx.x < NSTAGE) *reinterpret_cast<volatile unsigned*>(smem_raw + sm.pb_off + 4u * threadIdx.x) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sy_fence_async();
+    // row slabs with the halo push fused into the passes: a tile that stages rows (fine, or coarse for the
+    // prolongation) near a slab edge waits until the neighbour on that side has finished its previous pass
+    if (p.sync && threadIdx.x == 0) {
+        if (p.raise_up && tl.R0 - 8 < (int)p.own_lo) sy_wait_neighbour(p.sync, SYNC_PASS_UP);
+        if (p.raise_dn && tl.R1 + 8 > (int)p.own_hi) sy_wait_neighbour(p.sync, SYNC_PASS_DOWN);
+    }
     __syncthreads();
     const double acc = run_warp<ARITH, PRE, POSTK>(p, tl, geo, sm, warp, lane);
+    if (p.sync) {
+        // the stores of the tiles near a slab edge into the neighbours' memory (only those tiles pay for the
+        // system-scope fence), then (last CTA) the neighbours' arrival counters
+        const bool pushed = (p.raise_up && tl.rb0 < (int)(p.own_lo + 2 * p.push_rows + 2)) || (p.raise_dn && tl.rb1 > (int)(p.own_hi - 2 * p.push_rows - 2));
+        if (pushed) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned* ctas = reinterpret_cast<unsigned*>(p.sync + SYNC_PASS_CTAS);
+            if (atomicInc(ctas, gridDim.x - 1) == gridDim.x - 1) {      // wraps to 0 for the next pass
+                __threadfence_system();
+                if (p.raise_up) atomicAdd_system(p.raise_up, 1);
+                if (p.raise_dn) atomicAdd_system(p.raise_dn, 1);
+                p.sync[SYNC_PASSES_DONE] += 1;
+            }
+        }
+    }
     if (POSTK == POST_NORM2) {
         const double tot = block_sum(acc, scratch);
         if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
@@ -286,6 +321,9 @@ static int build_params(const StreamPassArgs& a, Params& p, unsigned& grid_out, 
     MGB_TRY(encode_field(&p.maps[FIELD_V2], a.v2, a.L.odd, a.L.pitch, p.rows_mem, pl.SWK, GROUP));
     if (a.coarse_u) MGB_TRY(encode_field(&p.maps[FIELD_C], a.coarse_u, a.Lc.odd, a.Lc.pitch, p.crows_mem, p.CW, CROWS));
     p.u_out = a.u_out; p.crhs = a.coarse_rhs; p.partials = a.partials;
+    p.peer_u_up = a.peer_u_up; p.peer_u_dn = a.peer_u_dn; p.peer_c_up = a.peer_c_up; p.peer_c_dn = a.peer_c_dn;
+    p.push_rows = a.push_rows; p.c_own_lo = a.c_own_lo; p.c_own_hi = a.c_own_hi;
+    p.sync = a.sync; p.raise_up = a.raise_up; p.raise_dn = a.raise_dn;
     if (p.post == POST_INJECT && !p.crhs) return fail(MGB200_ERR_INVALID, "stream_pass: POST_INJECT without coarse_rhs");
     if (p.post == POST_NORM2 && !p.partials) return fail(MGB200_ERR_INVALID, "stream_pass: POST_NORM2 without partials");
     grid_out = (unsigned)(pl.nstrips * pl.nbands);
@@ -311,6 +349,9 @@ int stream_pass(const StreamPassArgs& a, cudaStream_t s)
         key.iters = a.iters; key.coarse_u = a.coarse_u; key.Lc = a.Lc; key.post = a.post; key.coarse_rhs = a.coarse_rhs;
         key.partials = a.partials; key.arith = a.arith; key.own_lo = a.own_lo; key.own_hi = a.own_hi; key.row0 = a.row0;
         key.rows_mem = a.rows_mem; key.crow0 = a.crow0; key.crows_mem = a.crows_mem;
+        key.peer_u_up = a.peer_u_up; key.peer_u_dn = a.peer_u_dn; key.peer_c_up = a.peer_c_up; key.peer_c_dn = a.peer_c_dn;
+        key.push_rows = a.push_rows; key.c_own_lo = a.c_own_lo; key.c_own_hi = a.c_own_hi; key.sync = a.sync;
+        key.raise_up = a.raise_up; key.raise_dn = a.raise_dn;
         std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
         auto it = cache.find(k);
         if (it == cache.end()) {

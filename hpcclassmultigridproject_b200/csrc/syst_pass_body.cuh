@@ -93,6 +93,10 @@ struct Params {
     double* u_out;
     double* crhs;              // coarse rhs (POST_INJECT)
     double* partials;          // POST_NORM2
+    // halo push fused into the pass (stream_pass.cuh); peer_* are addressed by GLOBAL row: peer + row * pitch
+    double* peer_u_up; double* peer_u_dn; double* peer_c_up; double* peer_c_dn;
+    long push_rows, c_own_lo, c_own_hi;
+    int* sync; int* raise_up; int* raise_dn;
 };
 
 struct Tile {
@@ -163,6 +167,9 @@ struct Prog2 { unsigned h0, h1; };
 SY_FN void sy_prog_publish(const Smem& sm, int warp, unsigned steps_done);
 SY_FN Prog2 sy_prog_peek(const Smem& sm, int stage);
 SY_FN void sy_backoff(int ns);                           // between two unsuccessful peeks
+// row slabs: wait until arrival counter `slot` of the block `sync` has reached the number of passes this rank has
+// completed (one thread)
+SY_FN void sy_wait_neighbour(int* sync, int slot);
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes);
 SY_FN void sy_store_commit();
 SY_FN void sy_store_wait_read0();                        // every committed store has read its shared memory
@@ -452,9 +459,21 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
             if (EPI == POST_INJECT) {
                 // gs.cpp:283: coarse node (row/2, kg) for fine even column 2kg; kg even -> E run, kg+1 -> O run
                 const long kg = (long)tl.k0 + st.kk;
-                double* crow = p.crhs + ((long)(row >> 1) - p.crow0) * p.cpitch + (kg >> 1);
+                const long cr = row >> 1;
+                double* crow = p.crhs + (cr - p.crow0) * p.cpitch + (kg >> 1);
                 if (st.rmask0 & 1u) crow[0] = r0;
                 if (st.rmask0 & 2u) crow[p.codd] = r1;
+                // the slab neighbours' halo rows of the coarse right-hand side
+                if (p.peer_c_up && cr < p.c_own_lo + p.push_rows) {
+                    double* q = p.peer_c_up + cr * p.cpitch + (kg >> 1);
+                    if (st.rmask0 & 1u) q[0] = r0;
+                    if (st.rmask0 & 2u) q[p.codd] = r1;
+                }
+                if (p.peer_c_dn && cr > p.c_own_hi - p.push_rows) {
+                    double* q = p.peer_c_dn + cr * p.cpitch + (kg >> 1);
+                    if (st.rmask0 & 1u) q[0] = r0;
+                    if (st.rmask0 & 2u) q[p.codd] = r1;
+                }
             } else {
                 if (rm & 1u) st.acc += r0 * r0;
                 if (rm & 2u) st.acc += r1 * r1;
@@ -558,6 +577,18 @@ SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const 
             if (sy_elect()) {
                 if (nE8) sy_bulk_store(sm, gst, a, nE8);
                 if (nO8) sy_bulk_store(sm, gst + p.odd, a + geo.swkb, nO8);
+                // row slabs: the first / last rows this rank produces are the neighbours' halo rows: the same bulk
+                // copies, addressed to their memory (NVLink peer mapping), in the same group
+                if (p.peer_u_up && rs < p.own_lo + p.push_rows) {
+                    double* q = p.peer_u_up + (long)rs * p.pitch + tl.kb;
+                    if (nE8) sy_bulk_store(sm, q, a, nE8);
+                    if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
+                }
+                if (p.peer_u_dn && rs > p.own_hi - p.push_rows) {
+                    double* q = p.peer_u_dn + (long)rs * p.pitch + tl.kb;
+                    if (nE8) sy_bulk_store(sm, q, a, nE8);
+                    if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
+                }
                 sy_store_commit();
             }
         }

@@ -135,6 +135,7 @@ SY_FN void sy_backoff(int)
         std::abort();
     }
 }
+SY_FN void sy_wait_neighbour(int*, int) {}
 SY_FN void sy_bulk_store(const Smem& sm, double* gdst, unsigned soff, unsigned bytes) { std::memcpy(gdst, sm.raw + soff, bytes); }
 SY_FN void sy_store_commit() {}
 SY_FN void sy_store_wait_read0() {}
