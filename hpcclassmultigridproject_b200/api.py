@@ -21,7 +21,7 @@ class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("shape", C.c_int), ("niter", C.c_int), ("coarse_maxit", C.c_int),
                 ("coarse_tol", C.c_double), ("max_cycle", C.c_int), ("arith", C.c_int), ("plan", C.c_int),
                 ("correct_towers", C.c_int), ("use_graph", C.c_int), ("device", C.c_int), ("restriction", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("coarse_exact", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class SolveInfo(C.Structure):

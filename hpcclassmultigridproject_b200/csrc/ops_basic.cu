@@ -4,6 +4,8 @@
 // ROWS_PER_BLOCK rows x 256 columns; blockIdx.x indexes row groups (no 65535 limit), blockIdx.y
 // column chunks.  Every global access of a warp is a unit-stride run (split layout: one run
 // per parity).
+#include <mutex>
+
 #include "ops_basic.cuh"
 
 namespace mgb200 {
@@ -397,17 +399,134 @@ __global__ void __launch_bounds__(1024) k_coarse_solve(double* __restrict__ u, c
     if (threadIdx.x == 0 && iters_out) *iters_out = it;
 }
 
+// ---- opt-in direct solve of the coarsest level (the unfinished exact_solve.cpp:1-55 of the reference) -------------
+// Unknowns: the (n-1)^2 interior nodes, p = (i-1)(n-1) + (j-1); half bandwidth w = n-1; band storage
+// AB[p][w + q - p] for |q - p| <= w (row p of A, (2w+1) doubles per row).  LU without pivoting (A is strictly
+// diagonally dominant), multipliers stored in place of the eliminated entries.  One thread block; every
+// floating-point operation is a single rounded IEEE operation in a fixed order (the C restatement
+// orc_coarse_lu / orc_coarse_lu_solve of the oracle does the same operations in the same order).
+__global__ void __launch_bounds__(1024) k_coarse_lu_factor(double* __restrict__ ab, const double* __restrict__ v1,
+                                                           const double* __restrict__ v2, int n, Layout L, Stencil st)
+{
+    const int ni = n - 1, m = ni * ni, w = ni, bw = 2 * w + 1;
+    for (long q = threadIdx.x; q < (long)m * bw; q += blockDim.x) ab[q] = 0.0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < m; p += blockDim.x) {
+        const int i = 1 + p / ni, j = 1 + p % ni;
+        const long g = L.at(i, j);
+        const Coef4 c = Arith<MGB200_ARITH_EXACT>::coef(v1[g], v2[g], st);
+        double* row = ab + (long)p * bw + w;
+        row[0] = st.diag;
+        if (i > 1) row[-ni] = c.c;
+        if (i < n - 1) row[ni] = c.d;
+        if (j > 1) row[-1] = c.a;
+        if (j < n - 1) row[1] = c.b;
+    }
+    __syncthreads();
+    for (int k = 0; k < m - 1; ++k) {
+        const int rmax = min(w, m - 1 - k), nel = rmax * (rmax + 1);
+        const double pivot = ab[(long)k * bw + w];
+        // element e = (r, c) of the trailing update, r in 1..rmax, c in 0..rmax; c == 0 is the multiplier itself.
+        // At most 4 elements per thread (n <= 64: 63 * 64 <= 4 * 1024): read everything, barrier, write.
+        double val[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = (int)threadIdx.x + q * (int)blockDim.x;
+            val[q] = 0.0;
+            if (e < nel) {
+                const int r = 1 + e / (rmax + 1), c = e % (rmax + 1);
+                const double l = __ddiv_rn(ab[(long)(k + r) * bw + w - r], pivot);
+                val[q] = c ? __dsub_rn(ab[(long)(k + r) * bw + w - r + c], __dmul_rn(l, ab[(long)k * bw + w + c])) : l;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = (int)threadIdx.x + q * (int)blockDim.x;
+            if (e < nel) {
+                const int r = 1 + e / (rmax + 1), c = e % (rmax + 1);
+                ab[(long)(k + r) * bw + w - r + c] = val[q];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// u(interior) = A^-1 (rhs - boundary terms): forward substitution with the stored multipliers, back substitution
+// with U.  y lives in shared memory.
+__global__ void __launch_bounds__(128) k_coarse_lu_solve(double* __restrict__ u, const double* __restrict__ rhs,
+                                                         const double* __restrict__ v1, const double* __restrict__ v2,
+                                                         const double* __restrict__ ab, int n, Layout L, Stencil st, int zero_init)
+{
+    extern __shared__ double y[];
+    const int ni = n - 1, m = ni * ni, w = ni, bw = 2 * w + 1;
+    if (zero_init) {   // the boundary of a freshly zeroed level is zero (multigrid.cpp:77)
+        for (int q = threadIdx.x; q <= n; q += blockDim.x) { u[L.at(0, q)] = 0.0; u[L.at(n, q)] = 0.0; u[L.at(q, 0)] = 0.0; u[L.at(q, n)] = 0.0; }
+        __syncthreads();
+    }
+    for (int p = threadIdx.x; p < m; p += blockDim.x) {
+        const int i = 1 + p / ni, j = 1 + p % ni;
+        const long g = L.at(i, j);
+        const Coef4 c = Arith<MGB200_ARITH_EXACT>::coef(v1[g], v2[g], st);
+        double b = rhs[g];
+        // Dirichlet neighbours move to the right-hand side, in the order of gs.cpp:130 (north, west, south, east)
+        if (i == 1) b = __dsub_rn(b, __dmul_rn(c.c, u[L.at(0, j)]));
+        if (j == 1) b = __dsub_rn(b, __dmul_rn(c.a, u[L.at(i, 0)]));
+        if (i == n - 1) b = __dsub_rn(b, __dmul_rn(c.d, u[L.at(n, j)]));
+        if (j == n - 1) b = __dsub_rn(b, __dmul_rn(c.b, u[L.at(i, n)]));
+        y[p] = b;
+    }
+    __syncthreads();
+    for (int k = 0; k < m - 1; ++k) {                                  // L y = b
+        const int rmax = min(w, m - 1 - k);
+        const double yk = y[k];
+        for (int r = 1 + threadIdx.x; r <= rmax; r += blockDim.x) y[k + r] = __dsub_rn(y[k + r], __dmul_rn(ab[(long)(k + r) * bw + w - r], yk));
+        __syncthreads();
+    }
+    for (int k = m - 1; k >= 0; --k) {                                 // U x = y
+        const double xk = __ddiv_rn(y[k], ab[(long)k * bw + w]);
+        const int rmax = min(w, k);
+        __syncthreads();                                               // everybody has read y[k]
+        for (int r = 1 + threadIdx.x; r <= rmax; r += blockDim.x) y[k - r] = __dsub_rn(y[k - r], __dmul_rn(ab[(long)(k - r) * bw + w + r], xk));
+        if (threadIdx.x == 0) y[k] = xk;
+        __syncthreads();
+    }
+    for (int p = threadIdx.x; p < m; p += blockDim.x) u[L.at(1 + p / ni, 1 + p % ni)] = y[p];
+}
+
 }  // namespace
 
 int ops_basic_init()
 {
-    static bool done = false;
-    if (done) return MGB200_OK;
+    // function attributes are per device
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    MGB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && done[dev]) return MGB200_OK;
     const int smem = 4 * 65 * 65 * (int)sizeof(double);
     MGB_CUDA(cudaFuncSetAttribute(k_coarse_solve<MGB200_ARITH_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MGB_CUDA(cudaFuncSetAttribute(k_coarse_solve<MGB200_ARITH_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    done = true;
+    if (dev >= 0 && dev < 64) done[dev] = true;
     return MGB200_OK;
+}
+
+size_t coarse_lu_bytes(long n) { return (size_t)(n - 1) * (n - 1) * (2 * (n - 1) + 1) * sizeof(double); }
+
+int launch_coarse_lu_factor(double* ab, const double* v1, const double* v2, long n, Layout L, const Stencil& st, cudaStream_t s)
+{
+    if (n > 64 || n < 4) return fail(MGB200_ERR_INVALID, "coarse_lu: 4 <= n <= 64");
+    k_coarse_lu_factor<<<1, 1024, 0, s>>>(ab, v1, v2, (int)n, L, st);
+    return check_launch("k_coarse_lu_factor");
+}
+
+int launch_coarse_lu_solve(double* u, const double* rhs, const double* v1, const double* v2, const double* ab, long n, Layout L,
+                           const Stencil& st, bool zero_init, cudaStream_t s)
+{
+    if (n > 64 || n < 4) return fail(MGB200_ERR_INVALID, "coarse_lu: 4 <= n <= 64");
+    k_coarse_lu_solve<<<1, 128, (size_t)(n - 1) * (n - 1) * sizeof(double), s>>>(u, rhs, v1, v2, ab, (int)n, L, st, zero_init ? 1 : 0);
+    return check_launch("k_coarse_lu_solve");
 }
 
 // ---------------------------------------------------------------------------------------------

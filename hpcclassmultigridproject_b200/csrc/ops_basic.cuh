@@ -58,4 +58,11 @@ int launch_coarse_solve(double* u, const double* rhs, const double* v1, const do
                         const Stencil& st, int arith, bool zero_init, int maxit, double tol, int* iters_out,
                         cudaStream_t s);
 
+// opt-in direct coarsest-level solve (exact_solve.cpp:1-55): banded LU without pivoting of the (n-1)^2 interior
+// system in `ab` (coarse_lu_bytes(n) bytes of device memory), factor once per set of velocities, solve per visit
+size_t coarse_lu_bytes(long n);
+int launch_coarse_lu_factor(double* ab, const double* v1, const double* v2, long n, Layout L, const Stencil& st, cudaStream_t s);
+int launch_coarse_lu_solve(double* u, const double* rhs, const double* v1, const double* v2, const double* ab, long n, Layout L,
+                           const Stencil& st, bool zero_init, cudaStream_t s);
+
 }  // namespace mgb200

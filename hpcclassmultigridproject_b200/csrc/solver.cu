@@ -145,6 +145,7 @@ struct mgb200_solver {
     double* d_norm2 = nullptr;         // [0] current ||r||^2
     double* h_norm2 = nullptr;         // pinned mirror
     int* d_coarse_iters = nullptr;
+    double* d_coarse_lu = nullptr;     // opt-in direct coarsest solve: the factored band matrix (options.coarse_exact)
     double* d_flat[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec = nullptr;
     long graph_kernels = 0;
@@ -253,6 +254,7 @@ void mgb200_solver::release()
     cudaFree(d_partials); d_partials = nullptr;
     cudaFree(d_norm2); d_norm2 = nullptr;
     cudaFree(d_coarse_iters); d_coarse_iters = nullptr;
+    cudaFree(d_coarse_lu); d_coarse_lu = nullptr;
     cudaFree(d_flat[0]); cudaFree(d_flat[1]); d_flat[0] = d_flat[1] = nullptr;
     for (auto& t : d_top) { cudaFree(t); t = nullptr; }
     cudaFree(d_sync); d_sync = nullptr;
@@ -276,6 +278,7 @@ int mgb200_solver::init(long n, int maxlvl_, double nu_, double dt_, double dx_,
         return fail(MGB200_ERR_INVALID, "coarsest level must have n <= 64 (on-device coarse solve); raise maxlvl");
     if (opt.shape < 1 || opt.niter < 0 || opt.max_cycle < 0 || opt.max_cycle > 50)
         return fail(MGB200_ERR_INVALID, "bad options (shape >= 1, niter >= 0, 0 <= max_cycle <= 50)");
+    if (opt.coarse_exact != 0 && opt.coarse_exact != 1) return fail(MGB200_ERR_INVALID, "options.coarse_exact: 0 or 1");
     if (opt.restriction != 0 && (opt.restriction != 1 || opt.plan != MGB200_PLAN_UNFUSED))
         return fail(MGB200_ERR_INVALID, "options.restriction: 0 (injection) or 1 (full weighting, UNFUSED plan only)");
     if (P > 1 && (opt.plan != MGB200_PLAN_FUSED || opt.correct_towers))
@@ -711,8 +714,9 @@ int mgb200_solver::cycle_body(int l)
             // coarsest level: on-device loop {GS; residual; norm} (multigrid.cpp:55-65).  A level
             // entered from above starts from u = 0 (multigrid.cpp:77); the kernel zero-fills itself.
             const bool fresh = (l > 0 && rep == 0);
-            MGB_TRY(launch_coarse_solve(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, fresh,
-                                        opt.coarse_maxit, opt.coarse_tol, d_coarse_iters, stream));
+            if (opt.coarse_exact) MGB_TRY(launch_coarse_lu_solve(g.u[g.cur], g.rhs, g.v1, g.v2, d_coarse_lu, g.n, g.L, g.st, fresh, stream));
+            else MGB_TRY(launch_coarse_solve(g.u[g.cur], g.rhs, g.v1, g.v2, g.n, g.L, g.st, opt.arith, fresh,
+                                             opt.coarse_maxit, opt.coarse_tol, d_coarse_iters, stream));
             continue;
         }
         Level& c = lv[l + 1];
@@ -1168,6 +1172,12 @@ int mgb200_destroy(mgb200_solver* s)
 static int after_fields(mgb200_solver* s)
 {
     MGB_TRY(s->build_towers());
+    if (s->opt.coarse_exact && (s->P == 1 || s->rank == 0)) {
+        // the coarsest operator depends on the (new) velocities only: factor it once
+        Level& c = s->lv[s->maxlvl - 1];
+        if (!s->d_coarse_lu) MGB_CUDA(cudaMalloc(&s->d_coarse_lu, coarse_lu_bytes(c.n)));
+        MGB_TRY(launch_coarse_lu_factor(s->d_coarse_lu, c.v1, c.v2, c.n, c.L, c.st, s->stream));
+    }
     if (s->P > 1) {                    // the tower inputs are no longer needed
         MGB_CUDA(cudaStreamSynchronize(s->stream));
         for (auto& t : s->d_top) { cudaFree(t); t = nullptr; }

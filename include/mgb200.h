@@ -135,7 +135,11 @@ typedef struct mgb200_options {
     int    device;          /* CUDA device ordinal, -1 = current; default -1 */
     int    restriction;     /* 0 = injection of the residual (the reference, gs.cpp:283); 1 = full weighting
                                (gs.cpp:277-280, commented out there).  Opt-in, UNFUSED plan only; default 0 */
-    int    reserved[7];
+    int    coarse_exact;    /* 0 = coarsest level by iterated RB-GS (the reference, multigrid.cpp:55-65); 1 = direct
+                               solve by a banded LU factorisation without pivoting of the (n-1)^2 interior system
+                               (what exact_solve.cpp:1-55 set out to do with dgbtrf/dgbtrs; the matrix is strictly
+                               diagonally dominant, so partial pivoting would not exchange rows).  Opt-in; default 0 */
+    int    reserved[6];
 } mgb200_options;
 
 typedef struct mgb200_solve_info {

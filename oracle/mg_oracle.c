@@ -184,6 +184,7 @@ void orc_restriction_fw(double *coarse, const double *fine, long nf)
 struct orc_solver {
     long n;
     int maxlvl, shape;
+    int coarse_exact;          /* opt-in: direct solve of the coarsest level (orc_coarse_lu_solve) */
     double nu, dt, dx, tol;
     double *u[ORC_MAXLVL], *rhs[ORC_MAXLVL], *v1[ORC_MAXLVL], *v2[ORC_MAXLVL];
     double *tmp;
@@ -258,6 +259,62 @@ double *orc_level_v1 (orc_solver *s, int l) { return s->v1[l]; }
 double *orc_level_v2 (orc_solver *s, int l) { return s->v2[l]; }
 double *orc_tmp      (orc_solver *s)        { return s->tmp; }
 
+/* OPT-IN, no compiled-reference twin: exact_solve.cpp:1-55 of the reference (banded LU of the coarsest level through
+ * LAPACKE dgbtrf/dgbtrs) was never finished -- it does not compile and nothing calls it.  This is the direct solve it
+ * set out to do, written out so that the GPU kernel can be checked bit for bit: interior unknowns p = (i-1)(n-1)+(j-1),
+ * half bandwidth w = n-1, band storage ab[p][w+q-p], LU WITHOUT pivoting (the matrix is strictly diagonally dominant:
+ * partial pivoting would not exchange rows), k-outer elimination, then forward and back substitution.  Dirichlet
+ * neighbours move to the right-hand side in the order of gs.cpp:130 (north, west, south, east). */
+void orc_coarse_lu_solve(double *u, const double *f, long n, const double *v1, const double *v2,
+                         double dt, double nu, double dx)
+{
+    const long ni = n - 1, m = ni * ni, w = ni, bw = 2 * w + 1, ld = n + 1;
+    const double r = cn_ratio(dx, dt);
+    const double diag = 1.0 - 4.0 * r * nu;                    /* gs.cpp:75,130 */
+    double *ab = (double *)calloc((size_t)m * bw, sizeof(double));
+    double *y = (double *)calloc((size_t)m, sizeof(double));
+    for (long p = 0; p < m; ++p) {
+        const long i = 1 + p / ni, j = 1 + p % ni, g = i * ld + j;
+        const stencil_t c = stencil_at(v1, v2, g, nu, dx, r);
+        double *row = ab + p * bw + w;
+        row[0] = diag;
+        if (i > 1) row[-ni] = c.north;
+        if (i < n - 1) row[ni] = c.south;
+        if (j > 1) row[-1] = c.west;
+        if (j < n - 1) row[1] = c.east;
+        double b = f[g];
+        if (i == 1) b = b - c.north * u[(i - 1) * ld + j];
+        if (j == 1) b = b - c.west * u[i * ld + j - 1];
+        if (i == n - 1) b = b - c.south * u[(i + 1) * ld + j];
+        if (j == n - 1) b = b - c.east * u[i * ld + j + 1];
+        y[p] = b;
+    }
+    for (long k = 0; k < m - 1; ++k) {
+        const long rmax = w < m - 1 - k ? w : m - 1 - k;
+        const double pivot = ab[k * bw + w];
+        for (long rr = 1; rr <= rmax; ++rr) {
+            const double l = ab[(k + rr) * bw + w - rr] / pivot;
+            for (long c = 1; c <= rmax; ++c)
+                ab[(k + rr) * bw + w - rr + c] = ab[(k + rr) * bw + w - rr + c] - l * ab[k * bw + w + c];
+            ab[(k + rr) * bw + w - rr] = l;
+        }
+    }
+    for (long k = 0; k < m - 1; ++k) {
+        const long rmax = w < m - 1 - k ? w : m - 1 - k;
+        for (long rr = 1; rr <= rmax; ++rr) y[k + rr] = y[k + rr] - ab[(k + rr) * bw + w - rr] * y[k];
+    }
+    for (long k = m - 1; k >= 0; --k) {
+        const double xk = y[k] / ab[k * bw + w];
+        const long rmax = w < k ? w : k;
+        for (long rr = 1; rr <= rmax; ++rr) y[k - rr] = y[k - rr] - ab[(k - rr) * bw + w + rr] * xk;
+        y[k] = xk;
+    }
+    for (long p = 0; p < m; ++p) u[(1 + p / ni) * ld + 1 + p % ni] = y[p];
+    free(ab); free(y);
+}
+
+void orc_set_coarse_exact(orc_solver *s, int on) { s->coarse_exact = on; }
+
 /* mg_inner (multigrid.cpp:17-92).  Level l works on n_l = n >> l nodes per side
  * with spacing dx * 2^l; tmp is the single level-0 scratch re-read with the
  * stride of whichever level uses it. */
@@ -268,7 +325,9 @@ void orc_cycle(orc_solver *s, int l)
     double *u = s->u[l], *f = s->rhs[l], *v1 = s->v1[l], *v2 = s->v2[l];
 
     for (int rep = 0; rep < s->shape; ++rep) {                       /* :52 */
-        if (l == s->maxlvl - 1) {
+        if (l == s->maxlvl - 1 && s->coarse_exact) {
+            orc_coarse_lu_solve(u, f, nl, v1, v2, s->dt, s->nu, h);   /* opt-in, see above */
+        } else if (l == s->maxlvl - 1) {
             /* coarsest level: smooth until the ABSOLUTE residual norm drops (:58-65) */
             double rn = 1.0;
             for (int it = 0; it < ORC_COARSE_MAXIT && rn > ORC_COARSE_TOL; ++it) {

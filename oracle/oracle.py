@@ -74,6 +74,8 @@ class Oracle:
             L.orc_create.argtypes = [l, i, _dp, _dp, _dp, d, d, d, d, i]; L.orc_create.restype = C.c_void_p
             L.orc_destroy.argtypes = [C.c_void_p]
             L.orc_correct_towers.argtypes = [C.c_void_p]
+            L.orc_set_coarse_exact.argtypes = [C.c_void_p, i]
+            L.orc_coarse_lu_solve.argtypes = [_dp, _dp, l, _dp, _dp, d, d, d]
             L.orc_cycle.argtypes = [C.c_void_p, i]
             L.orc_form_rhs.argtypes = [C.c_void_p]
             L.orc_residual_norm.argtypes = [C.c_void_p]; L.orc_residual_norm.restype = d
@@ -217,7 +219,7 @@ class Towers:
 class OracleSolver:
     """orc_solver handle (mg_oracle.h) -- the restatement's driver with histories."""
 
-    def __init__(self, n, u0, v1, v2, nu, dt, dx, tol, shape=1, maxlvl=None, correct_towers=False):
+    def __init__(self, n, u0, v1, v2, nu, dt, dx, tol, shape=1, maxlvl=None, correct_towers=False, coarse_exact=False):
         self.o = Oracle()
         self.n = n
         self.maxlvl = maxlvl_for(n) if maxlvl is None else maxlvl
@@ -225,6 +227,8 @@ class OracleSolver:
         assert self.h
         if correct_towers:                # opt-in: true injection of the velocities (no reference twin)
             self.o.lib.orc_correct_towers(self.h)
+        if coarse_exact:                  # opt-in: direct solve of the coarsest level (no reference twin)
+            self.o.lib.orc_set_coarse_exact(self.h, 1)
 
     def close(self):
         if self.h:

@@ -200,6 +200,38 @@ def test_corrected_velocity_towers_option(mg, oracle, plan):
     o.close()
 
 
+@pytest.mark.parametrize("n,shape", [(64, 1), (256, 2), (1024, 1)])
+def test_exact_coarse_solve_option(mg, oracle, n, shape):
+    """options.coarse_exact = 1 (opt-in; what the reference's unfinished exact_solve.cpp:1-55 set out to do): the
+    coarsest level is solved directly by a banded LU without pivoting.  Bit-identical to the oracle's restatement of
+    the same factorisation on every level; the coarsest residual drops to rounding level; the outer iteration
+    converges to the same solution as the reference's iterated coarse solve in no more cycles."""
+    dx = 1.0 / n; dt = dx / 10; nu = -4e-4
+    u0, v1, v2 = oracle.initial_conditions(n, 2.0)
+    o = OracleSolver(n, u0, v1, v2, nu, dt, dx, 1e-12, shape, coarse_exact=True)
+    with mg.Solver(n, nu, dt, dx, 1e-12, shape=shape, arith=mg.ARITH_EXACT, coarse_exact=1) as s:
+        s.set_fields_host(u0, v1, v2)
+        o.form_rhs(); s.form_rhs()
+        for _ in range(2):
+            o.cycle(); s.cycle()
+            for l in range(s.maxlvl):
+                assert np.array_equal(s.level(l, "u"), o.u(l)), l
+        lc = s.maxlvl - 1
+        uc, fc, w1, w2 = (s.level(lc, k) for k in ("u", "rhs", "v1", "v2"))
+        nc = n >> lc
+        res = oracle.residual(uc, fc, nc, w1, w2, dt, nu, dx * (1 << lc))
+        assert oracle.norm(res, nc) <= 1e-13 * max(1e-300, np.abs(fc).max()) * nc
+    o.close()
+    outs = []
+    for exact in (0, 1):
+        with mg.Solver(n, nu, dt, dx, 1e-9, shape=shape, coarse_exact=exact) as s:
+            s.set_fields_host(u0, v1, v2)
+            infos = s.timestep(2)
+            outs.append((s.get_u_host(), [i.cycles for i in infos]))
+    assert rel_l2(outs[1][0], outs[0][0]) <= 1e-8
+    assert all(a <= b for a, b in zip(outs[1][1], outs[0][1]))
+
+
 def test_full_weighting_option(mg, oracle):
     """options.restriction = 1 (opt-in, UNFUSED plan): converges to the same solution as the reference's
     injection; rejected on the fused plan"""
