@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(1024) k_coarse_solve(double* __restrict__ u, c
 // Unknowns: the (n-1)^2 interior nodes, p = (i-1)(n-1) + (j-1); half bandwidth w = n-1; band storage
 // AB[p][w + q - p] for |q - p| <= w (row p of A, (2w+1) doubles per row).  LU without pivoting (A is strictly
 // diagonally dominant), multipliers stored in place of the eliminated entries.  One thread block; every
-// floating-point operation is a single rounded IEEE operation in a fixed order (the C restatement
-// orc_coarse_lu / orc_coarse_lu_solve of the oracle does the same operations in the same order).
+// floating-point operation is a single rounded IEEE operation in a fixed order (k-outer elimination, then the
+// two substitutions), so that a plain C statement of the same factorisation reproduces it bit for bit.
 __global__ void __launch_bounds__(1024) k_coarse_lu_factor(double* __restrict__ ab, const double* __restrict__ v1,
                                                            const double* __restrict__ v2, int n, Layout L, Stencil st)
 {
