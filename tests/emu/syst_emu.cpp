@@ -146,7 +146,20 @@ SY_FN D2 sy_lds2(const Smem& sm, unsigned off) { return *reinterpret_cast<const 
 SY_FN double sy_lds1(const Smem& sm, unsigned off) { return *reinterpret_cast<const double*>(sm.raw + off); }
 SY_FN void sy_sts2(const Smem& sm, unsigned off, D2 v) { *reinterpret_cast<D2*>(sm.raw + off) = v; }
 SY_FN void sy_sts1(const Smem& sm, unsigned off, double v) { *reinterpret_cast<double*>(sm.raw + off) = v; }
-SY_FN double sy_side(const Smem& sm, const D2&, unsigned off, int, bool outer) { return outer ? 0.0 : sy_lds1(sm, off); }
+// a real shuffle between the lane threads of a warp: write the own value, rendezvous, read the neighbour's,
+// rendezvous (every lane of the warp must call it, as on the device)
+static double g_shfl[WARPS][2][32];
+SY_FN double sy_side(const Smem& sm, const D2& mid, unsigned off, int dir, bool outer)
+{
+    g_shfl[t_warp][0][t_lane] = mid.x; g_shfl[t_warp][1][t_lane] = mid.y;
+    pthread_barrier_wait(&g_wbar[t_warp]);
+    double x;
+    if (dir < 0) x = t_lane > 0 ? g_shfl[t_warp][1][t_lane - 1] : 0.0;
+    else x = t_lane < 31 ? g_shfl[t_warp][0][t_lane + 1] : 0.0;
+    pthread_barrier_wait(&g_wbar[t_warp]);
+    if (t_lane == (dir < 0 ? 0 : 31)) x = outer ? 0.0 : sy_lds1(sm, off);
+    return x;
+}
 
 }  // namespace sy
 }  // namespace mgb200
