@@ -1446,7 +1446,8 @@ int mgb200_profile_level0(mgb200_solver* s, int reps, double* ms_a, double* byte
 // The reference's timestepper allocates and frees its towers on every call (multigrid.cpp:138-162,
 // 177-185).  Allocating and zero-filling ~14 GB of HBM per call would dominate an N=16384 call, so
 // the one-call drivers keep the last handle alive and reuse it when the next call has the same
-// shape and parameters; mgb200_release_cached() frees it.
+// shape and parameters; mgb200_release_cached() frees it, and with MGB200_TIMESTEPPER_CACHE=0 in the
+// environment nothing is kept at all.
 namespace {
 struct CachedHandle {
     std::mutex mu;
@@ -1486,7 +1487,9 @@ static int timestepper_common(double* uT, const double* u0, const double* v1, co
     }
     if (rc == MGB200_OK) rc = host ? mgb200_get_u_host(s, uT) : mgb200_get_u_device(s, uT, n + 1);   // :175
     if (last) *last = info;
-    if (rc != MGB200_OK) { mgb200_destroy(s); g_cached.s = nullptr; }
+    // MGB200_TIMESTEPPER_CACHE=0: free everything on return, as the reference does (multigrid.cpp:177-185)
+    const char* keep = getenv("MGB200_TIMESTEPPER_CACHE");
+    if (rc != MGB200_OK || (keep && keep[0] == '0')) { mgb200_destroy(s); g_cached.s = nullptr; }
     return rc;
 }
 

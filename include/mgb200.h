@@ -282,7 +282,8 @@ int mgb200_host_prolongation(double *up, const double *u, int n);   /* n = COARS
 int mgb200_host_restriction(double *u, const double *up, int n);    /* n = FINE n   (gs.h:17) */
 
 /* The one-call drivers keep their last handle (the level towers in HBM) alive and reuse it when
- * the next call has the same shape and parameters; this frees it. */
+ * the next call has the same shape and parameters; this frees it.  MGB200_TIMESTEPPER_CACHE=0 in the
+ * environment makes the drivers free everything on return, like multigrid.cpp:177-185. */
 int mgb200_release_cached(void);
 
 #ifdef __cplusplus

@@ -116,6 +116,26 @@ def test_timestepper_entry_point(mg, oracle, plan):
     assert np.array_equal(u0, u0b)
 
 
+def test_timestepper_frees_its_towers_on_request(mg, oracle, monkeypatch):
+    """MGB200_TIMESTEPPER_CACHE=0: the one-call driver keeps no handle alive (multigrid.cpp:177-185 frees everything)"""
+    import torch
+    n = 1024; dx = 1.0 / n; dt = dx / 10
+    u0, v1, v2 = oracle.initial_conditions(n)
+    uT = np.zeros_like(u0)
+    mg.release_cached()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    mg.timestepper_host(uT, u0, v1, v2, -4e-4, mg.maxlvl_for(n), n, dt, 2 * dt, dx, 1e-6, 1)
+    kept = free0 - torch.cuda.mem_get_info()[0]
+    assert kept > 5 * 8 * (n + 1) ** 2            # the towers of the cached handle
+    mg.release_cached()
+    monkeypatch.setenv("MGB200_TIMESTEPPER_CACHE", "0")
+    uT2 = np.zeros_like(u0)
+    mg.timestepper_host(uT2, u0, v1, v2, -4e-4, mg.maxlvl_for(n), n, dt, 2 * dt, dx, 1e-6, 1)
+    assert free0 - torch.cuda.mem_get_info()[0] < kept // 4
+    assert np.array_equal(uT, uT2)
+
+
 @pytest.mark.parametrize("plan", PLANS)
 def test_graph_replay_equals_direct_launch(mg, oracle, plan):
     n = 256; dx = 1.0 / n; dt = dx / 10
