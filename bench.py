@@ -251,6 +251,10 @@ def run_own(args, rank, world):
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    # host buffers of the e2e leg next to this rank's GPU (undone before the CPU leg, which uses every core)
+    from hpcclassmultigridproject_b200.affinity import bind_near_gpu
+    all_cpus = os.sched_getaffinity(0)
+    affinity = None if os.environ.get("MGB200_BENCH_NO_AFFINITY") else bind_near_gpu(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -397,6 +401,7 @@ def run_own(args, rank, world):
     if world > 1:
         s.close()
 
+    os.sched_setaffinity(0, all_cpus)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         ms, kind, cores, sample, extra = cpu_vcycle_ms(n, 2, 1, budget_s=60.0)
@@ -420,7 +425,7 @@ def run_own(args, rank, world):
                          "kernel": ("level-0 streaming pass (3 RB-GS iterations fused with residual+injection / "
                                     "prolong+correct+norm)") if args.plan == "fused" else "level-0 colour half-sweep + residual",
                          "launch_ms": [ms_a, ms_b], "launch_bytes": [by_a, by_b]},
-            "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clk.summary(), "gpu_launches": int(launches), "e2e": e2e, "host_affinity": affinity, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if dist:

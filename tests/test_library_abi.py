@@ -65,3 +65,15 @@ def test_options_struct_layout_matches_header(libpath):
     assert o.struct_size == ctypes.sizeof(mg.Options)
     assert (o.shape, o.niter, o.coarse_maxit, o.max_cycle) == (1, 3, 1000, 50)    # multigrid.cpp:41,60,94
     assert o.coarse_tol == 1e-5 and o.correct_towers == 0
+
+
+def test_host_affinity_helper_is_harmless_without_topology():
+    """hpcclassmultigridproject_b200/affinity.py: cpulist parser; no GPU / one NUMA node -> nothing is changed, nothing raised"""
+    import os
+    from hpcclassmultigridproject_b200.affinity import bind_near_gpu, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    r = bind_near_gpu(0)
+    assert r is None or set(os.sched_getaffinity(0)) <= set(before)
+    os.sched_setaffinity(0, before)
