@@ -323,3 +323,33 @@ def test_linearity_of_the_cycle(mg):
             base = u
         else:
             assert np.array_equal(u, 2.0 * base)
+
+
+@pytest.mark.parametrize("swk", [32, 64, 96])
+def test_every_strip_width_gives_the_same_field(swk, tmp_path):
+    """MGB200_SWK pins the strip width of the streaming pass (one warp per role for <= 64 pairs, a partly filled second
+    warp at 96): the result does not depend on it, bit for bit (exact arithmetic, two time steps at N=1024)"""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import hpcclassmultigridproject_b200 as mg\n"
+        "from oracle.oracle import Oracle\n"
+        "n = 1024; dx = 1.0 / n; dt = dx / 10\n"
+        "u0, v1, v2 = Oracle().initial_conditions(n)\n"
+        "with mg.Solver(n, -4e-4, dt, dx, 1e-10, arith=mg.ARITH_EXACT, plan=mg.PLAN_FUSED) as s:\n"
+        "    s.set_fields_host(u0, v1, v2)\n"
+        "    infos = s.timestep(2)\n"
+        "    print(hashlib.sha256(s.get_u_host().tobytes()).hexdigest(), [i.cycles for i in infos])\n" % ROOT)
+    outs = []
+    for env_swk in (None, str(swk)):
+        env = dict(os.environ)
+        env.pop("MGB200_SWK", None)
+        if env_swk:
+            env["MGB200_SWK"] = env_swk
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
