@@ -442,7 +442,9 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
             if (okb & 2u) sy_sts1(sm, c + 8u, o1);
         }
         // the row is written: publish (the last stage's rows go to the bulk-store engine: generic -> async proxy first)
+#ifndef SY_FENCE_IN_PRODUCER
         if (LAST) sy_fence_async();
+#endif
         publish(sm, st, k);
         if (NORM1 && row >= st.elo && row <= st.ehi) {
             // gs.cpp:75 on the nodes just updated, every operand in registers (owned nodes are never masked)
@@ -566,44 +568,67 @@ SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const 
     const unsigned nE8 = (unsigned)(((eE - tl.kb + 1) & ~1L) * 8);   // whole 16-byte units (the layout has slack)
     const unsigned nO8 = (unsigned)((eO - tl.kb) * 8);
     int rs = tl.R0 - off_s, rl = tl.R0 - off_l;                      // the rows of the two roles in step 0
-    double* gst = p.u_out + ((long)rs - p.row0) * p.pitch + tl.kb;
+    const long pitch = p.pitch;
+    double* gstE = p.u_out + ((long)rs - p.row0) * pitch + tl.kb;    // destinations of the row's two runs
+    double* gstO = gstE + p.odd;
     unsigned a = (unsigned)((((rs - tl.R0) % RING) + RING) % RING) * geo.rowb + (unsigned)HK * 8u;
+    const unsigned awrap = geo.ringb + (unsigned)HK * 8u;
     const unsigned need_h1 = geo.nh == 2 ? 1u : 0u;
+    const bool push = p.peer_u_up != nullptr || p.peer_u_dn != nullptr;
+    Prog2 seen_s{0u, 0u};
     for (int k = 0; k <= klast; ++k, ++rs, ++rl) {
         const bool store = rs >= tl.rb0 && rs <= tl.rb1;
+        // the stores are committed (one bulk group) when the stored row closes a ring group: the rows stored after it
+        // (rs > rl with an epilogue) stay in the open group, which the wait before a refill does not cover
+        const bool commit = ((rs - tl.R0) & (GROUP - 1)) == GROUP - 1;
         const bool load = gnext < ng && rl >= tl.R0 + GROUP * gnext - RING + GROUP - 1;
-        if (store) {
-            prog_wait(sm, pair_s, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_s));
-            if (sy_elect()) {
-                if (nE8) sy_bulk_store(sm, gst, a, nE8);
-                if (nO8) sy_bulk_store(sm, gst + p.odd, a + geo.swkb, nO8);
+        // (the last stage is usually more than one row ahead: the counters are read again only when the values seen
+        // last do not cover this row)
+        if (store && (seen_s.h0 < (unsigned)k + 1u || seen_s.h1 < need_h1 * ((unsigned)k + 1u))) {
+            seen_s = sy_prog_peek(sm, pair_s);
+            while (seen_s.h0 < (unsigned)k + 1u || seen_s.h1 < need_h1 * ((unsigned)k + 1u)) { sy_backoff(geo.backoff_ns); seen_s = sy_prog_peek(sm, pair_s); }
+        }
+        if ((store || commit) && sy_elect()) {
+            if (store) {
+#ifdef SY_FENCE_IN_PRODUCER
+                sy_fence_async();                                    // the stages' stores (acquired above) -> the engine's reads
+#endif
+                if (nE8) sy_bulk_store(sm, gstE, a, nE8);
+                if (nO8) sy_bulk_store(sm, gstO, a + geo.swkb, nO8);
                 // row slabs: the first / last rows this rank produces are the neighbours' halo rows: the same bulk
                 // copies, addressed to their memory (NVLink peer mapping), in the same group
-                if (p.peer_u_up && rs < p.own_lo + p.push_rows) {
-                    double* q = p.peer_u_up + (long)rs * p.pitch + tl.kb;
-                    if (nE8) sy_bulk_store(sm, q, a, nE8);
-                    if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
+                if (push) {
+                    if (p.peer_u_up && rs < p.own_lo + p.push_rows) {
+                        double* q = p.peer_u_up + (long)rs * pitch + tl.kb;
+                        if (nE8) sy_bulk_store(sm, q, a, nE8);
+                        if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
+                    }
+                    if (p.peer_u_dn && rs > p.own_hi - p.push_rows) {
+                        double* q = p.peer_u_dn + (long)rs * pitch + tl.kb;
+                        if (nE8) sy_bulk_store(sm, q, a, nE8);
+                        if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
+                    }
                 }
-                if (p.peer_u_dn && rs > p.own_hi - p.push_rows) {
-                    double* q = p.peer_u_dn + (long)rs * p.pitch + tl.kb;
-                    if (nE8) sy_bulk_store(sm, q, a, nE8);
-                    if (nO8) sy_bulk_store(sm, q + p.odd, a + geo.swkb, nO8);
-                }
-                sy_store_commit();
             }
+            if (commit) sy_store_commit();
         }
         if (load) {
             prog_wait(sm, pair_l, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_l));
-            // stores of rows <= rl must have left shared memory; the newest one (row rs > rl with an epilogue) may be in flight
-            if (sy_elect()) { if (store && epi) sy_store_wait_read1(); else sy_store_wait_read0(); }
+            // the committed stores (rows <= rl at the last commit) must have left shared memory
+            if (sy_elect()) {
+                sy_store_wait_read0();
+#ifdef SY_FENCE_IN_PRODUCER
+                sy_fence_async();                                    // the stages' stores into the slots -> the engine's writes
+#endif
+            }
             issue_group_loads(p, tl, geo, sm, gnext);
             ++gnext;
         }
-        gst += p.pitch;
+        gstE += pitch; gstO += pitch;
         a += geo.rowb;
-        if (a >= geo.ringb + (unsigned)HK * 8u) a -= geo.ringb;
+        if (a >= awrap) a -= geo.ringb;
     }
-    if (sy_elect()) sy_store_wait_all();
+    if (sy_elect()) { sy_store_commit(); sy_store_wait_all(); }
 }
 
 // the work of one warp on one tile; returns the thread's share of the POST_NORM2 sum
