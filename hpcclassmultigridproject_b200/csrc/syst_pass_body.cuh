@@ -552,7 +552,10 @@ SY_FN void issue_group_loads(const Params& p, const Tile& tl, const Geo& geo, co
 // ROLE (the EPI role if the pass has one, else the last stage): once it has published its step on row rl it needs
 // no row <= rl any more (what it still uses of row rl+1 it carries in registers), so group g (first row G), which
 // replaces rows G-RING .. G-RING+GROUP-1, is requested once row G-RING+GROUP-1 is published -- after the bulk stores
-// issued so far have read their rows.
+// of those rows have read them.  The stores are committed as ONE bulk group per ring group (a commit per row flushes
+// the TMA command queue every row and made this warp, whose per-row path paces the pipeline together with the last
+// stage, measurably slower): the commit follows the store of the group's last row, so the rows stored after it
+// belong to the open group and are not waited for.
 SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
 {
     const int ng = num_groups(tl);
