@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_syst_pass(const __grid_constant_
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < NGROUP)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm.base32 + sm.full_off + 8u * threadIdx.x) : "memory");
-    if (threadIdx.x < NSTAGE) *reinterpret_cast<volatile unsigned*>(smem_raw + sm.pb_off + 4u * threadIdx.x) = 0u;
+    if (threadIdx.x < NPROG) *reinterpret_cast<volatile unsigned*>(smem_raw + sm.pb_off + 4u * threadIdx.x) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sy_fence_async();
     // row slabs with the halo push fused into the passes: a tile that stages rows (fine, or coarse for the

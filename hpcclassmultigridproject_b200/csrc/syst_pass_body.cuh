@@ -59,9 +59,11 @@ constexpr int KMAX = 3;
 constexpr int NSTW = 2;        // warps per half-sweep stage (64 pairs each)
 constexpr int NPAIR = 2 * KMAX + 2;      // half-sweep stages + the prolongation role + the residual role
 constexpr int NSTAGE = NPAIR * NSTW;      // warps of those roles (a progress counter each)
-constexpr int WARPS = NSTAGE + 1;
+constexpr int WARPS = NSTAGE + 2;          // + the load warp + the store warp
 constexpr int THREADS = WARPS * 32;
-constexpr int PRODUCER_WARP = NSTAGE;
+constexpr int PRODUCER_WARP = NSTAGE;      // requests the TMA groups
+constexpr int STORE_WARP = NSTAGE + 1;     // hands finished rows to the bulk-store engine
+constexpr int NPROG = NSTAGE + 2;          // progress counters: the role warps' + a pair slot for the store warp
 // opaque storage for a CUtensorMap (128 bytes, 64-byte aligned); filled by the host launcher
 struct alignas(64) TensorMapStorage { unsigned long long q[16]; };
 
@@ -119,7 +121,7 @@ enum Field { FIELD_U = 0, FIELD_F = 1, FIELD_V1 = 2, FIELD_V2 = 3, FIELD_C = 4 }
 
 constexpr size_t smem_bytes(int swk)
 {
-    return (size_t)4 * RING * 2 * swk * 8 + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8) * 8 + NGROUP * 8 + NSTAGE * 4 + 128;
+    return (size_t)4 * RING * 2 * swk * 8 + (size_t)NGROUP * CROWS * 2 * (swk / 2 + 8) * 8 + NGROUP * 8 + NPROG * 4 + 128;
 }
 constexpr size_t SMEM_BYTES = smem_bytes(SWK_MAX);
 
@@ -224,7 +226,7 @@ SY_FN int num_groups(const Tile& tl) { return (tl.R1 - tl.R0) / GROUP + 1; }
 //            injection of the even columns of even rows, or sum of squares (the second colour's
 //            residual is summed by the last stage itself: all its operands are in registers)      off = off(last) + 2
 // Pair index in the progress counters: stage s -> s, PRE -> 2 KMAX, EPI -> 2 KMAX + 1.
-constexpr int PAIR_PRE = 2 * KMAX, PAIR_EPI = 2 * KMAX + 1;
+constexpr int PAIR_PRE = 2 * KMAX, PAIR_EPI = 2 * KMAX + 1, PAIR_STORE = NPAIR;
 
 SY_FN int off_stage(const Params& p, int s) { return 1 + 2 * s + (p.pre ? 1 : 0); }
 SY_FN int off_epi(const Params& p) { return off_stage(p, 2 * p.K - 1) + 2; }
@@ -441,10 +443,9 @@ SY_FN void stage_step(const Params& p, const Tile& tl, const Geo& geo, const Sme
             if (okb & 1u) sy_sts1(sm, c, o0);
             if (okb & 2u) sy_sts1(sm, c + 8u, o1);
         }
-        // the row is written: publish (the last stage's rows go to the bulk-store engine: generic -> async proxy first)
-#ifndef SY_FENCE_IN_PRODUCER
-        if (LAST) sy_fence_async();
-#endif
+        // the row is written: publish.  (The last stage's rows go to the bulk-store engine; the generic -> async proxy
+        // fence that must lie between these stores and the engine's reads is executed by the STORE warp, after it has
+        // acquired this publication: in the stage it cost the one role that never waits for anybody a fifth of its step.)
         publish(sm, st, k);
         if (NORM1 && row >= st.elo && row <= st.ehi) {
             // gs.cpp:75 on the nodes just updated, every operand in registers (owned nodes are never masked)
@@ -547,30 +548,28 @@ SY_FN void issue_group_loads(const Params& p, const Tile& tl, const Geo& geo, co
     }
 }
 
-// The producer follows the last stage and the last role.  In step k the last stage finishes row rs = t - off(last):
-// the row is stored as soon as both of its warps have published the step.  Ring rows are released by the LAST
-// ROLE (the EPI role if the pass has one, else the last stage): once it has published its step on row rl it needs
-// no row <= rl any more (what it still uses of row rl+1 it carries in registers), so group g (first row G), which
-// replaces rows G-RING .. G-RING+GROUP-1, is requested once row G-RING+GROUP-1 is published -- after the bulk stores
-// of those rows have read them.  The stores are committed as ONE bulk group per ring group (a commit per row flushes
-// the TMA command queue every row and made this warp, whose per-row path paces the pipeline together with the last
-// stage, measurably slower): the commit follows the store of the group's last row, so the rows stored after it
-// belong to the open group and are not waited for.
-SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
+// Two single warps drain and feed the ring (warp-uniform code, one elected lane issues).
+//
+// The STORE warp follows the last stage.  In step k that stage finishes row rs = t - off(last): the row goes to the
+// bulk-store engine as soon as both of its warps have published the step -- after the generic -> async proxy fence,
+// executed here, on the acquiring side (see stage_step).  The stores are committed as ONE bulk group
+// per ring group (a commit per row flushes the TMA command queue every row); after the commit the warp waits until the
+// engine has read the group's rows and publishes the number of groups done in its own counter.
+//
+// The LOAD warp follows the last ROLE (the EPI role if the pass has one, else the last stage), which releases the ring
+// rows: once it has published its step on row rl it needs no row <= rl any more (what it still uses of row rl+1 it
+// carries in registers), so group g (first row G), which replaces rows G-RING .. G-RING+GROUP-1 (ring group g - NGROUP),
+// is requested once row G-RING+GROUP-1 is published and the store warp has counted that group.
+SY_FN void store_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
 {
-    const int ng = num_groups(tl);
-    int gnext = 0;
-    for (; gnext < ng && gnext < NGROUP; ++gnext) issue_group_loads(p, tl, geo, sm, gnext);   // fresh slots
     const int klast = last_step(p, tl) - tl.R0;
     const int pair_s = 2 * p.K - 1, off_s = off_stage(p, pair_s);
-    const bool epi = p.post != POST_NONE;
-    const int pair_l = epi ? PAIR_EPI : pair_s, off_l = epi ? off_epi(p) : off_s;
     long eE = (long)tl.kb + p.WK, eO = eE;
     if (eE > p.nhalf + 1) eE = p.nhalf + 1;
     if (eO > p.nhalf) eO = p.nhalf;
     const unsigned nE8 = (unsigned)(((eE - tl.kb + 1) & ~1L) * 8);   // whole 16-byte units (the layout has slack)
     const unsigned nO8 = (unsigned)((eO - tl.kb) * 8);
-    int rs = tl.R0 - off_s, rl = tl.R0 - off_l;                      // the rows of the two roles in step 0
+    int rs = tl.R0 - off_s;                                          // the last stage's row in step 0
     const long pitch = p.pitch;
     double* gstE = p.u_out + ((long)rs - p.row0) * pitch + tl.kb;    // destinations of the row's two runs
     double* gstO = gstE + p.odd;
@@ -579,23 +578,20 @@ SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const 
     const unsigned need_h1 = geo.nh == 2 ? 1u : 0u;
     const bool push = p.peer_u_up != nullptr || p.peer_u_dn != nullptr;
     Prog2 seen_s{0u, 0u};
-    for (int k = 0; k <= klast; ++k, ++rs, ++rl) {
+    unsigned groups = 0;
+    for (int k = 0; k <= klast; ++k, ++rs) {
         const bool store = rs >= tl.rb0 && rs <= tl.rb1;
-        // the stores are committed (one bulk group) when the stored row closes a ring group: the rows stored after it
-        // (rs > rl with an epilogue) stay in the open group, which the wait before a refill does not cover
-        const bool commit = ((rs - tl.R0) & (GROUP - 1)) == GROUP - 1;
-        const bool load = gnext < ng && rl >= tl.R0 + GROUP * gnext - RING + GROUP - 1;
+        const bool close = rs >= tl.R0 && ((rs - tl.R0) & (GROUP - 1)) == GROUP - 1;     // the row closes a ring group
         // (the last stage is usually more than one row ahead: the counters are read again only when the values seen
         // last do not cover this row)
-        if (store && (seen_s.h0 < (unsigned)k + 1u || seen_s.h1 < need_h1 * ((unsigned)k + 1u))) {
+        if ((store || close) && (seen_s.h0 < (unsigned)k + 1u || seen_s.h1 < need_h1 * ((unsigned)k + 1u))) {
             seen_s = sy_prog_peek(sm, pair_s);
             while (seen_s.h0 < (unsigned)k + 1u || seen_s.h1 < need_h1 * ((unsigned)k + 1u)) { sy_backoff(geo.backoff_ns); seen_s = sy_prog_peek(sm, pair_s); }
         }
-        if ((store || commit) && sy_elect()) {
+        if (close) ++groups;
+        if ((store || close) && sy_elect()) {
             if (store) {
-#ifdef SY_FENCE_IN_PRODUCER
                 sy_fence_async();                                    // the stages' stores (acquired above) -> the engine's reads
-#endif
                 if (nE8) sy_bulk_store(sm, gstE, a, nE8);
                 if (nO8) sy_bulk_store(sm, gstO, a + geo.swkb, nO8);
                 // row slabs: the first / last rows this rank produces are the neighbours' halo rows: the same bulk
@@ -613,25 +609,39 @@ SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const 
                     }
                 }
             }
-            if (commit) sy_store_commit();
-        }
-        if (load) {
-            prog_wait(sm, pair_l, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_l));
-            // the committed stores (rows <= rl at the last commit) must have left shared memory
-            if (sy_elect()) {
+            if (close) {
+                sy_store_commit();
                 sy_store_wait_read0();
-#ifdef SY_FENCE_IN_PRODUCER
-                sy_fence_async();                                    // the stages' stores into the slots -> the engine's writes
-#endif
+                sy_prog_publish(sm, 2 * PAIR_STORE, groups);
             }
-            issue_group_loads(p, tl, geo, sm, gnext);
-            ++gnext;
         }
         gstE += pitch; gstO += pitch;
         a += geo.rowb;
         if (a >= awrap) a -= geo.ringb;
     }
-    if (sy_elect()) { sy_store_commit(); sy_store_wait_all(); }
+    if (sy_elect()) { sy_store_commit(); sy_store_wait_all(); sy_prog_publish(sm, 2 * PAIR_STORE, groups + 64u); }
+}
+
+SY_FN void producer_loop(const Params& p, const Tile& tl, const Geo& geo, const Smem& sm)
+{
+    const int ng = num_groups(tl);
+    int gnext = 0;
+    for (; gnext < ng && gnext < NGROUP; ++gnext) issue_group_loads(p, tl, geo, sm, gnext);   // fresh slots
+    const int klast = last_step(p, tl) - tl.R0;
+    const int pair_s = 2 * p.K - 1, off_s = off_stage(p, pair_s);
+    const bool epi = p.post != POST_NONE;
+    const int pair_l = epi ? PAIR_EPI : pair_s, off_l = epi ? off_epi(p) : off_s;
+    const unsigned need_h1 = geo.nh == 2 ? 1u : 0u;
+    int rl = tl.R0 - off_l;                                          // the last role's row in step 0
+    for (int k = 0; k <= klast && gnext < ng; ++k, ++rl) {
+        if (rl < tl.R0 + GROUP * gnext - RING + GROUP - 1) continue;
+        prog_wait(sm, pair_l, (unsigned)k + 1u, need_h1 * ((unsigned)k + 1u), sy_prog_peek(sm, pair_l));
+        // ring group gnext - NGROUP must have left shared memory: the store warp has counted gnext - NGROUP + 1 groups
+        prog_wait(sm, PAIR_STORE, (unsigned)(gnext - NGROUP + 1), 0u, sy_prog_peek(sm, PAIR_STORE));
+        if (sy_elect()) sy_fence_async();                            // the stages' stores into the slots -> the engine's writes
+        issue_group_loads(p, tl, geo, sm, gnext);
+        ++gnext;
+    }
 }
 
 // the work of one warp on one tile; returns the thread's share of the POST_NORM2 sum
@@ -645,6 +655,13 @@ SY_FN double run_warp(const Params& p, const Tile& tl, const Geo& geo, const Sme
         if (lane != 0) return 0.0;
 #endif
         producer_loop(p, tl, geo, sm);
+        return 0.0;
+    }
+    if (warp == STORE_WARP) {
+#ifdef SY_HOST_MODEL
+        if (lane != 0) return 0.0;
+#endif
+        store_loop(p, tl, geo, sm);
         return 0.0;
     }
     const int pair = warp / NSTW, h = warp % NSTW;
@@ -664,7 +681,8 @@ SY_FN double run_warp(const Params& p, const Tile& tl, const Geo& geo, const Sme
     }
     if (pair > last) return 0.0;
     Stage st = init_role(p, tl, geo, pair, pair == 0 ? (PRE ? PAIR_PRE : -1) : pair - 1, pair, off_stage(p, pair), h, lane);
-    if (pair == last) stage_loop<ARITH, true, POSTK == POST_NORM2, false, POST_NONE>(p, tl, geo, sm, st);
+    // (the last stage differs from the others only where it sums its own residual)
+    if (pair == last && POSTK == POST_NORM2) stage_loop<ARITH, true, true, false, POST_NONE>(p, tl, geo, sm, st);
     else stage_loop<ARITH, false, false, false, POST_NONE>(p, tl, geo, sm, st);
     return st.acc;
 }

@@ -51,7 +51,7 @@ static pthread_barrier_t g_wbar[WARPS];
 // mbarrier model: completed-phase count; arrival count 1 (+ transaction bytes for the full barriers)
 struct MBar { std::atomic<unsigned long> phases{0}; std::atomic<long> tx{0}; };
 static MBar g_full[NGROUP];
-static std::atomic<unsigned> g_prog[NSTAGE];       // steps completed per stage warp
+static std::atomic<unsigned> g_prog[NPROG];       // steps completed per stage warp
 static std::atomic<long> g_spins{0};
 static int g_jitter = 0;
 
