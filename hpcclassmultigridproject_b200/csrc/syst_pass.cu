@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_syst_pass(const __grid_constant_
     const Tile tl = make_tile(p, blockIdx.x);
     const Geo geo = make_geo(p);
     // warp index through a shuffle: provably warp-uniform, so that role branches are uniform and
-    // the producer's operands live in uniform registers
+    // the load and store warps' operands live in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < NGROUP)

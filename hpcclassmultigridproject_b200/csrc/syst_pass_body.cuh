@@ -19,7 +19,8 @@
 //
 //     stage s, step k   needs   stage s-1 (both column halves), step k-1          [row below + strip-half edge]
 //     stage 0           needs   the TMA group of its lower row                     [full barriers]
-//     producer, step k  needs   the last stage, step k                             [row to store, ring slots to refill]
+//     store warp, step k needs  the last stage, step k                             [row to hand to the bulk-store engine]
+//     load warp, step k  needs  the last role, step k, and the store warp's count  [ring slots to refill]
 //
 // The reverse (write-after-read) hazards are implied by these: stage s+1 cannot touch a row before
 // stage s has finished the row below it, and by then stage s has long read everything it needs of
@@ -37,7 +38,7 @@
 // (Folding both into stage 0 and the last stage saves shared-memory traffic but makes those two warps do 2-3
 // times the work of the others, and the pipeline runs at the pace of its slowest warp: measured slower.)
 //
-// Warps: 2 per role (64 column pairs each, one 16-byte vector = 2 nodes per lane) + 1 producer.
+// Warps: 2 per role (64 column pairs each, one 16-byte vector = 2 nodes per lane) + the load warp + the store warp.
 #pragma once
 #include "common.cuh"
 #include "stream_pass.cuh"
@@ -520,7 +521,7 @@ SY_FN void stage_loop(const Params& p, const Tile& tl, const Geo& geo, const Sme
 }
 
 // ------------------------------------------------------------------------------------------
-// producer: request group g (first memory row z) into its ring slot: the four fields plus the three
+// load warp: request group g (first memory row z) into its ring slot: the four fields plus the three
 // coarse rows its prolongation needs, all completing on the slot's full barrier; then start the HBM
 // fetch of the group after next, whose shared-memory request will hit L2.  Whole (converged) warp,
 // warp-uniform operands; one elected lane issues.
